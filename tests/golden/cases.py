@@ -1,0 +1,54 @@
+"""Shared, seeded input builders for the golden vectors (used by make_golden.py and by the tests).
+
+Everything is regenerated from seeds -- only OUTPUTS of the reference are stored in the .npz files.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from iris_b200 import scenes
+from oracle import field as OF
+
+
+def golden_params(seed=1):
+    """A 'trained-looking' BRDF field: Xavier MLP, grid values U(-0.5,0.5) so that albedo / roughness /
+    metallic vary over the scene (tcnn's own init U(+-1e-4) gives a constant 0.5 everywhere)."""
+    p = OF.init_params(0)
+    g = torch.Generator().manual_seed(seed)
+    p[OF.N_MLP:] = (torch.rand(OF.N_GRID, generator=g) * 2 - 1) * 0.5
+    return p
+
+
+CASES = {
+    # name: scene, image side, spp, SLF H, sample seed, extra uniform columns
+    "small": dict(scene="cornell", side=16, spp=4, H=64, useed=5, depth=2),
+    "c1": dict(scene="cornell", side=64, spp=16, H=256, useed=11, depth=0),
+}
+
+
+def build(name):
+    c = dict(CASES[name])
+    sc = scenes.cornell(seed=0)
+    rays = sc.camera_rays(c["side"], c["side"])
+    rng = np.random.default_rng(c["useed"])
+    n = c["side"] * c["side"] * c["spp"]
+    U = rng.random((n, 8 + 6 * c["depth"]), dtype=np.float32)
+    # the reference hazard u > cdf[K-1] is never injected
+    U = np.minimum(U, np.float32(0.99999))
+    Gw = rng.standard_normal((c["side"] * c["side"], 3)).astype(np.float32)
+    c.update(sc=sc, rays=rays, U=U, Gw=Gw, params=golden_params())
+    return c
+
+
+def grid_fingerprint(g):
+    """Compact summary of a 28M-entry gradient: per-level sums + the 4096 largest-magnitude entries."""
+    g = np.asarray(g, np.float64)
+    lv_sum, lv_abs = [], []
+    for (_, _, size, off) in OF.LEVELS:
+        s = g[off * 2:(off + size) * 2]
+        lv_sum.append(s.sum())
+        lv_abs.append(np.abs(s).sum())
+    top = np.argsort(-np.abs(g))[:4096]
+    top.sort()
+    return np.array(lv_sum), np.array(lv_abs), top.astype(np.int64), g[top].astype(np.float32)

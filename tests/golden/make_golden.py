@@ -1,0 +1,77 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own estimators (imported from
+/root/reference with the two absent third-party engines substituted, see oracle/refharness.py)
+on the seeded inputs of tests/golden/cases.py.  Runs only in the build container:
+
+    PYTHONPATH=. python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import refharness as RH                    # noqa: E402
+from oracle.intersect import OracleScene               # noqa: E402
+from tests.golden import cases                         # noqa: E402
+
+
+def single_with_grads(c, osc):
+    em = RH.make_emitter(c["sc"], c["H"], learn=True)
+    mat = RH.make_material(c["sc"], c["params"])
+    U = torch.as_tensor(c["U"][:, :8])
+    L = RH.run_single(osc, em, mat, c["rays"], c["spp"], U)
+    (L * torch.as_tensor(c["Gw"])).sum().backward()
+    K = c["sc"].n_emitters
+    gp = mat.mlp.params.grad.numpy()
+    assert np.isfinite(gp).all()
+    lv_sum, lv_abs, top_i, top_v = cases.grid_fingerprint(gp[9216:])
+    return dict(L=L.detach().numpy(), d_radiance=em.radiance.grad[:K].numpy(),
+                d_radiance_rest_absmax=np.float32(em.radiance.grad[K:].abs().max().item()),
+                d_mlp=gp[:9216], d_grid_level_sum=lv_sum, d_grid_level_abs=lv_abs, d_grid_top_idx=top_i, d_grid_top_val=top_v)
+
+
+def main():
+    out = {}
+    # ---------------- small: every estimator
+    c = cases.build("small")
+    osc = OracleScene(c["sc"].vertices, c["sc"].faces)
+    r = torch.as_tensor(c["rays"])
+    U = torch.as_tensor(c["U"])
+    g = single_with_grads(c, osc)
+    em = RH.make_emitter(c["sc"], c["H"], learn=False)
+    mat = RH.make_material(c["sc"], c["params"])
+    pos, nrm, uv, tri, valid = osc.ray_intersect(r[:, 0:3], r[:, 3:6])
+    raw = osc.intersect_raw(c["rays"][:, 0:3], c["rays"][:, 3:6], "brute")
+    g.update(prim=raw["prim"], t=raw["t"], uv=raw["uv"], p=raw["p"], n=raw["n"])
+    g["L_full"] = RH.run_full(osc, em, mat, c["rays"], c["spp"], c["depth"], U).numpy()
+    tri2 = tri.clone()
+    tri2[5] = -1
+    tri2[100] = -1
+    Ud = U[:, :2 + 6 * c["depth"]]
+    g["det_diff"] = RH.run_det_diff(osc, em, mat, pos, r[:, 3:6], nrm, tri2, c["spp"], c["depth"], Ud).numpy()
+    levels = torch.linspace(0.02, 1.0, 6)
+    for i in (0, 2, 5):
+        a0, a1 = RH.run_det_spec(osc, em, mat, levels[i], pos, r[:, 3:6], nrm, tri2, c["spp"], c["depth"], Ud)
+        g["det_spec0_%d" % i], g["det_spec1_%d" % i] = a0.numpy(), a1.numpy()
+    g["bake_diff"] = RH.run_bake(osc, em, pos, nrm, -r[:, 3:6], c["spp"], U[:, :2]).numpy()
+    for i in range(6):
+        a0, a1 = RH.run_bake(osc, em, pos, nrm, -r[:, 3:6], c["spp"], U[:, :2], level=levels[i])
+        g["bake_spec0_%d" % i], g["bake_spec1_%d" % i] = a0.numpy(), a1.numpy()
+    np.savez_compressed(os.path.join(HERE, "small.npz"), **g)
+    print("small.npz", {k: v.shape for k, v in g.items()})
+
+    # ---------------- C1: Cornell 64x64 spp 16, path_tracing_single fwd + bwd (BASELINE.json configs[0])
+    c = cases.build("c1")
+    osc = OracleScene(c["sc"].vertices, c["sc"].faces)
+    g = single_with_grads(c, osc)
+    np.savez_compressed(os.path.join(HERE, "c1.npz"), **g)
+    print("c1.npz", {k: v.shape for k, v in g.items()})
+
+
+if __name__ == "__main__":
+    main()

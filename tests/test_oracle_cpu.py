@@ -1,0 +1,151 @@
+"""CPU suite: pins oracle/ (the checker) against the golden vectors produced by the REFERENCE's own
+code (tests/golden/make_golden.py) and checks the oracle's internal consistency."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import estimators as E
+from oracle import field as OF
+from oracle.intersect import OracleScene
+from tests.golden import cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _setup(name, learn=False):
+    c = cases.build(name)
+    osc = OracleScene(c["sc"].vertices, c["sc"].faces)
+    em = E.Emitter(c["sc"].emitter_dict(), c["sc"].slf_dict(c["H"]), learn=learn)
+    vmin, vmax = c["sc"].voxel_bounds()
+    p = c["params"].clone().requires_grad_(learn)
+    mat_fn = lambda x: OF.material(x, p, vmin, vmax)
+    r = torch.as_tensor(c["rays"])
+    return c, osc, em, p, mat_fn, r, torch.as_tensor(c["U"])
+
+
+def test_level_table_matches_survey():
+    # levels 0-6 dense with these entry counts, 13 977 056 entries in total
+    sizes = [s for (_, _, s, _) in OF.LEVELS]
+    assert sizes[:7] == [4096, 9264, 21952, 46656, 97336, 216000, 474552]
+    assert all(s == 1 << 19 for s in sizes[7:])
+    assert OF.N_ENTRIES == 13977056 and OF.N_PARAMS == 27954112 + 9216
+
+
+def test_bvh_matches_brute_force():
+    c = cases.build("small")
+    sc = c["sc"]
+    osc = OracleScene(sc.vertices, sc.faces)
+    rng = np.random.default_rng(3)
+    n = 4000
+    o = rng.uniform(-0.9, 0.9, (n, 3)).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # rays that start ON surfaces (secondary-ray pattern) and rays aimed at mesh vertices (edge/vertex ties)
+    a = osc.intersect_raw(o, d, "brute")
+    o2 = (a["p"] + np.float32(E.RAY_EPSILON) * a["n"]).astype(np.float32)
+    tgt = sc.vertices[rng.integers(0, len(sc.vertices), n)]
+    d3 = tgt - o
+    d3 /= np.linalg.norm(d3, axis=1, keepdims=True)
+    for oo, dd in ((o, d), (o2, a["n"]), (o, d3.astype(np.float32))):
+        x = osc.intersect_raw(oo, dd, "brute")
+        y = osc.intersect_raw(oo, dd, "bvh")
+        assert (x["prim"] == y["prim"]).all()
+        assert (x["t"] == y["t"]).all() and (x["p"] == y["p"]).all() and (x["n"] == y["n"]).all()
+    assert a["tie"].sum() == 0
+    # Moller-Trumbore is not watertight: a ray aimed exactly at a shared vertex may slip between triangles.
+    # That is part of the DEFINED semantics (CPU oracle == CUDA kernel); it must stay rare even for such rays.
+    x = osc.intersect_raw(o, d3.astype(np.float32), "brute")
+    assert (x["prim"] < 0).mean() < 0.1
+    assert (osc.intersect_raw(o, d, "brute")["prim"] >= 0).all()
+
+
+def test_miss_and_empty():
+    sc = cases.build("small")["sc"]
+    osc = OracleScene(sc.vertices[:3], np.array([[0, 1, 2]], np.int32))
+    o = np.array([[5, 5, 5]], np.float32)
+    d = np.array([[1, 0, 0]], np.float32)
+    r = osc.intersect_raw(o, d)
+    assert r["prim"][0] == -1 and np.isinf(r["t"][0]) and (r["p"] == 0).all() and (r["n"] == 0).all()
+    r = osc.intersect_raw(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert len(r["prim"]) == 0
+
+
+def test_small_golden_all_estimators(relclose):
+    g = np.load(os.path.join(GOLD, "small.npz"))
+    c, osc, em, p, mat_fn, r, U = _setup("small")
+    raw = osc.intersect_raw(c["rays"][:, 0:3], c["rays"][:, 3:6], "bvh")
+    assert (raw["prim"] == g["prim"]).all() and (raw["t"] == g["t"]).all()
+    assert (raw["p"] == g["p"]).all() and (raw["n"] == g["n"]).all() and (raw["uv"] == g["uv"]).all()
+    o, d, dx, dy = r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12]
+    spp, depth = c["spp"], c["depth"]
+    with torch.no_grad():
+        pos, nrm, _, tri, _ = osc.ray_intersect(o, d)
+        tri2 = tri.clone()
+        tri2[5] = -1
+        tri2[100] = -1
+        checks = {
+            "L": E.path_tracing_single(osc, em, mat_fn, o, d, dx, dy, spp, U[:, :8]),
+            "L_full": E.path_tracing(osc, em, mat_fn, o, d, dx, dy, spp, depth, U),
+            "det_diff": E.path_tracing_det_diff(osc, em, mat_fn, pos, d, nrm, tri2, spp, depth, U[:, :2 + 6 * depth]),
+            "bake_diff": E.bake_diffuse(osc, em, pos, nrm, spp, U[:, :2]),
+        }
+        levels = torch.linspace(0.02, 1.0, 6)
+        for i in (0, 2, 5):
+            a0, a1 = E.path_tracing_det_spec(osc, em, mat_fn, levels[i], pos, d, nrm, tri2, spp, depth, U[:, :2 + 6 * depth])
+            checks["det_spec0_%d" % i], checks["det_spec1_%d" % i] = a0, a1
+        for i in range(6):
+            a0, a1 = E.bake_specular(osc, em, pos, -d, nrm, levels[i], spp, U[:, :2])
+            checks["bake_spec0_%d" % i], checks["bake_spec1_%d" % i] = a0, a1
+    for k, v in checks.items():
+        frac, worst = relclose(v.numpy(), g[k], rtol=1e-5)
+        assert frac == 1.0, (k, frac, worst)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_single_forward_backward_golden(name, relclose):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    c, osc, em, p, mat_fn, r, U = _setup(name, learn=True)
+    L = E.path_tracing_single(osc, em, mat_fn, r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], c["spp"], U[:, :8])
+    frac, worst = relclose(L.detach().numpy(), g["L"], rtol=1e-5)
+    assert frac == 1.0, (frac, worst)
+    (L * torch.as_tensor(c["Gw"])).sum().backward()
+    K = c["sc"].n_emitters
+    # emitter radiance: only rows [0,K) receive gradient
+    frac, worst = relclose(em.radiance.grad[:K].numpy(), g["d_radiance"], rtol=1e-4)
+    assert frac == 1.0, worst
+    assert float(em.radiance.grad[K:].abs().max()) == 0.0 and float(g["d_radiance_rest_absmax"]) == 0.0
+    # BRDF field: the reference differentiates sigmoid in fp16, the oracle in fp32 (straight-through), so compare at
+    # 2e-3 of the largest entry
+    gp = p.grad.numpy()
+    scale = np.abs(g["d_mlp"]).max()
+    assert np.abs(gp[:9216] - g["d_mlp"]).max() <= 2e-3 * scale
+    lv_sum, lv_abs, top_i, top_v = cases.grid_fingerprint(gp[9216:])
+    assert np.allclose(lv_abs, g["d_grid_level_abs"], rtol=5e-3)
+    gv = gp[9216:][g["d_grid_top_idx"]]
+    assert np.abs(gv - g["d_grid_top_val"]).max() <= 2e-3 * np.abs(g["d_grid_top_val"]).max()
+
+
+def test_brdf_gradient_finite_differences():
+    """fp64-free sanity of the analytic BRDF derivative the adjoint kernel uses: torch autograd of eval_brdf vs
+    central differences in float64."""
+    torch.manual_seed(0)
+    n = 64
+    def rnd_dir():
+        v = torch.randn(n, 3, dtype=torch.float64)
+        v[:, 2] = v[:, 2].abs() + 0.1
+        return v / v.norm(dim=-1, keepdim=True)
+    wi, wo = rnd_dir(), rnd_dir()
+    nrm = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64).expand(n, 3)
+    x = torch.rand(n, 5, dtype=torch.float64) * 0.8 + 0.1
+    x.requires_grad_(True)
+    f = lambda x: E.eval_brdf(wi, wo, nrm, {"albedo": x[:, 0:3], "roughness": x[:, 3:4], "metallic": x[:, 4:5]})[0]
+    w = torch.randn(n, 3, dtype=torch.float64)
+    (f(x) * w).sum().backward()
+    h = 1e-6
+    for k in range(5):
+        e = torch.zeros(5, dtype=torch.float64)
+        e[k] = h
+        fd = ((f(x.detach() + e) - f(x.detach() - e)) * w).sum(-1) / (2 * h)
+        assert torch.allclose(fd, x.grad[:, k], rtol=1e-5, atol=1e-7)
