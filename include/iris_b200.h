@@ -1,0 +1,167 @@
+/*
+ * iris_b200.h -- C ABI of libiris_b200.so, the B200-native (sm_100a) replacement for the
+ * differentiable Monte-Carlo shading hot path of facebookresearch/iris.
+ *
+ * The reference has no native code and no FFI: its hot path is Python that calls Mitsuba/OptiX
+ * (ray casts) and tiny-cuda-nn (BRDF field) and ~300 ATen kernels per estimator call
+ * (SURVEY.md section 2a).  Each entry point below therefore replaces a reference PYTHON interface,
+ * cited as file:line relative to the reference tree; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All array arguments are DEVICE pointers on the scene's device unless a
+ *     parameter is documented as host.  `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *     default stream).  Calls are asynchronous on that stream.
+ *   - every function returns 0 on success or a negative IrisStatus; iris_last_error() returns a
+ *     thread-local message (the reference raises Python exceptions / asserts).
+ *   - the library allocates device memory only in iris_scene_create (the BVH); per-call scratch is a
+ *     caller-provided workspace whose size iris_*_workspace_bytes reports.
+ *   - n == 0 is a successful no-op everywhere (the reference's early returns on empty lane sets,
+ *     utils/path_tracing.py:72-73,153-154,241-242,347-348).
+ */
+#ifndef IRIS_B200_H
+#define IRIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum IrisStatus {
+    IRIS_OK = 0,
+    IRIS_ERR_INVALID = -1,   /* bad argument */
+    IRIS_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    IRIS_ERR_NOMEM = -3,
+    IRIS_ERR_WORKSPACE = -4  /* workspace too small */
+} IrisStatus;
+
+const char *iris_last_error(void);
+/* "iris_b200 <version> sm_100a" */
+const char *iris_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene: one triangle mesh + 8-wide compressed BVH resident in HBM.
+ * Replaces mitsuba.load_dict({'type':'scene','shape_id':{'type':'obj'|'ply',...}})
+ * (train_emitter.py:57-63, bake_shading.py:55-61); prim index = face order of `faces`.
+ * verts/faces are HOST pointers.  builder: 0 = host binned-SAH (default), 1 = on-device LBVH.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct IrisScene IrisScene;
+
+typedef struct IrisSceneStats {
+    int64_t n_tris;
+    int64_t n_nodes;        /* 80-byte BVH8 nodes */
+    int64_t node_bytes;
+    int64_t tri_bytes;      /* 48-byte triangle records */
+    float build_ms;
+    float sah_cost;
+    int32_t max_depth;      /* levels of 8-wide nodes (<= 32, the traversal stack) */
+    float bounds_lo[3], bounds_hi[3];
+} IrisSceneStats;
+
+int iris_scene_create(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces,
+                      int device, int builder, IrisScene **out);
+void iris_scene_destroy(IrisScene *scene);
+int iris_scene_stats(const IrisScene *scene, IrisSceneStats *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * iris_intersect -- closest hit of n rays.  Replaces ray_intersect(scene,xs,ds)
+ * (utils/path_tracing.py:17-48): t (n) [inf on miss], prim (n) [-1 on miss], uv (n,2) barycentrics,
+ * p (n,3) hit point, nrm (n,3) unit geometric normal flipped toward -d (utils/ops.py:85-96).
+ * Any output pointer may be NULL.  Semantics are bit-for-bit those of oracle/intersect.c.
+ * ---------------------------------------------------------------------------------------------- */
+int iris_intersect(const IrisScene *scene, const float *o, const float *d, int64_t n,
+                   float *t, int32_t *prim, float *uv, float *p, float *nrm, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Shading tables (device pointers, owned by the caller).
+ * Emitter part: SLFEmitter buffers (model/emitter.py:136-173).  SLF part: VoxelSLF (model/slf.py:30-39)
+ * with `inds` narrowed to int32.  Field part: NGPBRDF (model/brdf.py:213-260) = tcnn HashGrid+MLP
+ * parameters at fp16 (`grid` N_ENTRIES x 2, `mlp` 9216, layout [W1|W2|W3] row-major [out][in]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct IrisShadeParams {
+    /* emitters */
+    const int32_t *emitter_of_face;   /* (F)  emitter index or -1            (is_emitter + emitter_idx) */
+    const int32_t *face_of_emitter;   /* (K)  triangle_idx                                              */
+    const float *emitter_vertices;    /* (K,3,3)                                                        */
+    const float *emitter_area;        /* (K)                                                            */
+    const float *emitter_pdf;         /* (K)  1/K                                                       */
+    const float *emitter_cdf;         /* (K)  fp32 cumsum of emitter_pdf                                */
+    const float *radiance;            /* (>=K,3) rows [0,K) are read                     */
+    int32_t n_emitters;               /* K */
+    int32_t n_faces;                  /* F */
+    /* surface light field */
+    const int32_t *slf_inds;          /* (H,H,H) [z][y][x], -1 = empty */
+    const float *slf_radiance;        /* (n_occ,3) */
+    int32_t slf_H;
+    float slf_vmin, slf_range;        /* fp32(voxel_min), fp32(voxel_max - voxel_min) */
+    /* BRDF field (may be NULL for the bake entry points) */
+    const void *grid_f16;             /* __half[N_ENTRIES*2] */
+    const void *mlp_f16;              /* __half[9216] */
+    float field_vmin, field_range;
+} IrisShadeParams;
+
+/* Uniform samples: an explicit buffer U[(lane*stride)+column] (parity mode: identical injected
+ * sequences) or, when U == NULL, Philox-4x32-10 keyed by (seed, lane + lane_offset, column/4). */
+typedef struct IrisSampler {
+    const float *U;
+    int32_t stride;
+    uint64_t seed;
+    uint64_t lane_offset;
+} IrisSampler;
+
+/* Fills out[n*dims] with the uniforms the Philox mode would hand to lanes [0,n) (tests use it to run the
+ * oracle on the production stream). */
+int iris_sampler_fill(uint64_t seed, uint64_t lane_offset, int64_t n, int32_t dims, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Shading-map bake -- the inner loops of bake_shading.py:108-123 (diffuse) and :168-188 (specular):
+ * per pixel, spp importance-sampled secondary rays from (position,normal), emitter radiance or SLF at
+ * the hit, mean over spp.  mode 0: out0 = Ld (B,3).  mode 1: out0 = Ls0, out1 = Ls1 for `roughness`.
+ * wo is ignored for mode 0.  Uses sampler columns 0..1.
+ * ---------------------------------------------------------------------------------------------- */
+int iris_bake(const IrisScene *scene, const IrisShadeParams *params, int mode, float roughness,
+              const float *position, const float *normal, const float *wo, int64_t n_pixels, int32_t spp,
+              const IrisSampler *sampler, float *out0, float *out1, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BRDF field -- NGPBRDF.forward (model/brdf.py:243-260): mat (n,5) = albedo rgb, roughness, metallic.
+ * iris_field_backward accumulates d_params (fp32, [mlp 9216 | grid N_ENTRIES*2], same flat layout as the
+ * tcnn parameter vector `mlp.params`) given d_mat (n,5); d_params must be zero-initialised by the caller
+ * (or hold a running sum).
+ * ---------------------------------------------------------------------------------------------- */
+/* Hash-grid level table (32 entries each): returns the total number of grid entries (13 977 056). */
+int64_t iris_field_levels(float *scale, uint32_t *res, uint32_t *size, uint32_t *offset);
+int iris_field_forward(const IrisShadeParams *params, const float *position, int64_t n, float *mat, void *stream);
+int iris_field_backward(const IrisShadeParams *params, const float *position, const float *d_mat, int64_t n,
+                        float *d_params, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * path_tracing_single forward + adjoint (utils/path_tracing.py:320-407), the estimator
+ * train_emitter.py:184-189 and initialize.py:175-180 differentiate.
+ *   rays: (B,12) = o,d,dxdu,dydv (utils/dataset/synthetic_ldr.py:50-57); L (B,3) = mean over spp.
+ *   Sampler columns: 0 du,1 dv,2 e1,3 e2x,4 e2y,5 b1,6 b2x,7 b2y.
+ *   record: NULL for inference; otherwise >= iris_single_record_bytes(B,spp) bytes that the adjoint
+ *   replays (per sample: emitter rows + coefficients of the three radiance gathers, and the 3x3
+ *   sparse Jacobian of the sample's radiance wrt albedo/roughness/metallic).
+ *   workspace: >= iris_single_workspace_bytes(B,spp).
+ * iris_single_backward: dL (B,3) -> d_radiance (K,3) accumulated; d_mat (B*spp,5) written (feed it,
+ * with `x0` = the primary hit positions held in the record, to iris_field_backward via
+ * iris_single_backward's d_params argument: when d_params != NULL the field adjoint is run too).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp);
+int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp);
+int iris_single_forward(const IrisScene *scene, const IrisShadeParams *params, const float *rays,
+                        int64_t n_pixels, int32_t spp, const IrisSampler *sampler, float *L,
+                        void *record, void *workspace, int64_t workspace_bytes, void *stream);
+int iris_single_backward(const IrisShadeParams *params, const float *dL, int64_t n_pixels, int32_t spp,
+                         const void *record, float *d_radiance, float *d_params,
+                         void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t iris_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRIS_B200_H */

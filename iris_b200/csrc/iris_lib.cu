@@ -1,0 +1,280 @@
+// iris_lib.cu -- the C ABI of libiris_b200.so (include/iris_b200.h): argument checking, launches, error strings.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/iris_b200.h"
+#include "bvh8.h"
+#include "field.cuh"
+#include "kernels.cuh"
+
+struct IrisScene {
+    int device = 0;
+    float4 *nodes = nullptr;
+    float4 *tris = nullptr;
+    IrisSceneStats stats{};
+};
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t e__ = (x);                                                                              \
+        if (e__ != cudaSuccess) return fail(IRIS_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+#define LAUNCHED()                                                                                                   \
+    do {                                                                                                             \
+        g_launches.fetch_add(1);                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                                        \
+        if (e__ != cudaSuccess) return fail(IRIS_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + IRIS_BLOCK - 1) / IRIS_BLOCK); }
+static inline SceneView view_of(const IrisScene *s) {
+    SceneView v;
+    v.nodes = s->nodes;
+    v.tris = s->tris;
+    v.n_tris = s->stats.n_tris;
+    return v;
+}
+
+static int g_sm_count = 0;
+static bool g_field_ready[64] = {false};
+static int ensure_device_setup(int device) {
+    if (device < 0 || device >= 64) return fail(IRIS_ERR_INVALID, "device index out of range");
+    if (g_field_ready[device]) return IRIS_OK;
+    FieldLevel lv[FIELD_LEVELS];
+    field_level_table(lv);
+    CUDA_TRY(cudaMemcpyToSymbol(c_levels, lv, sizeof(lv)));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    g_sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaFuncSetAttribute(k_single_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * IRIS_BWD_KMAX * IRIS_BLOCK * 4));
+    g_field_ready[device] = true;
+    return IRIS_OK;
+}
+
+extern "C" {
+
+const char *iris_last_error(void) { return g_err.c_str(); }
+const char *iris_version(void) { return "iris_b200 0.1 sm_100a"; }
+int64_t iris_launch_count(void) { return g_launches.load(); }
+
+int64_t iris_field_levels(float *scale, uint32_t *res, uint32_t *size, uint32_t *offset) {
+    FieldLevel lv[FIELD_LEVELS];
+    const int64_t total = field_level_table(lv);
+    for (int l = 0; l < FIELD_LEVELS; ++l) {
+        if (scale) scale[l] = lv[l].scale;
+        if (res) res[l] = lv[l].res;
+        if (size) size[l] = lv[l].size;
+        if (offset) offset[l] = lv[l].offset;
+    }
+    return total;
+}
+
+int iris_scene_create(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces, int device, int builder, IrisScene **out) {
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!verts || !faces))) return fail(IRIS_ERR_INVALID, "bad mesh arguments");
+    if (n_faces > 0x7FFFFFF0ll / 3) return fail(IRIS_ERR_INVALID, "too many faces");
+    if (builder != 0) return fail(IRIS_ERR_INVALID, "builder 1 (on-device LBVH) is not available in this build");
+    for (int64_t i = 0; i < 3 * n_faces; ++i)
+        if (faces[i] < 0 || faces[i] >= n_verts) return fail(IRIS_ERR_INVALID, "face index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    int rc = ensure_device_setup(device);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    HostBvh hb;
+    if (host_bvh_build(verts, n_verts, faces, n_faces, &hb) != 0) return fail(IRIS_ERR_NOMEM, "host BVH build failed");
+    if (hb.max_depth > IRIS_STACK) {
+        host_bvh_free(&hb);
+        return fail(IRIS_ERR_INVALID, "BVH deeper than the traversal stack (" + std::to_string(hb.max_depth) + " levels)");
+    }
+    IrisScene *s = new IrisScene();
+    s->device = device;
+    const size_t nb = sizeof(Bvh8Node) * (size_t)hb.n_nodes, tb = sizeof(TriRecord) * (size_t)(hb.n_tris > 0 ? hb.n_tris : 1);
+    cudaError_t e = cudaMalloc(&s->nodes, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&s->tris, tb);
+    if (e == cudaSuccess) e = cudaMemcpy(s->nodes, hb.nodes, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && hb.n_tris > 0) e = cudaMemcpy(s->tris, hb.tris, sizeof(TriRecord) * (size_t)hb.n_tris, cudaMemcpyHostToDevice);
+    s->stats.n_tris = hb.n_tris;
+    s->stats.n_nodes = hb.n_nodes;
+    s->stats.node_bytes = (int64_t)nb;
+    s->stats.tri_bytes = (int64_t)(sizeof(TriRecord) * (size_t)hb.n_tris);
+    s->stats.sah_cost = hb.sah_cost;
+    s->stats.max_depth = hb.max_depth;
+    for (int k = 0; k < 3; ++k) { s->stats.bounds_lo[k] = hb.lo[k]; s->stats.bounds_hi[k] = hb.hi[k]; }
+    host_bvh_free(&hb);
+    if (e != cudaSuccess) {
+        cudaFree(s->nodes);
+        cudaFree(s->tris);
+        delete s;
+        return fail(IRIS_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    }
+    s->stats.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = s;
+    return IRIS_OK;
+}
+
+void iris_scene_destroy(IrisScene *s) {
+    if (!s) return;
+    cudaFree(s->nodes);
+    cudaFree(s->tris);
+    delete s;
+}
+
+int iris_scene_stats(const IrisScene *s, IrisSceneStats *out) {
+    if (!s || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    *out = s->stats;
+    return IRIS_OK;
+}
+
+int iris_intersect(const IrisScene *s, const float *o, const float *d, int64_t n, float *t, int32_t *prim, float *uv, float *p, float *nrm,
+                   void *stream) {
+    if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
+    if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
+    if (n == 0) return IRIS_OK;
+    if (!o || !d) return fail(IRIS_ERR_INVALID, "ray arrays are NULL");
+    k_intersect<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+__global__ void k_sampler_fill(IrisSampler smp, int64_t n, int dims, float *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int b = 0; 4 * b < dims; ++b) {
+        const float4 u = sample4(smp, i, b);
+        const float v[4] = {u.x, u.y, u.z, u.w};
+        for (int k = 0; k < 4 && 4 * b + k < dims; ++k) out[i * dims + 4 * b + k] = v[k];
+    }
+}
+
+int iris_sampler_fill(uint64_t seed, uint64_t lane_offset, int64_t n, int32_t dims, float *out, void *stream) {
+    if (n < 0 || dims <= 0 || !out) return fail(IRIS_ERR_INVALID, "bad sampler_fill arguments");
+    if (n == 0) return IRIS_OK;
+    IrisSampler smp{nullptr, 0, seed, lane_offset};
+    k_sampler_fill<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(smp, n, dims, out);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+static int check_params(const IrisShadeParams *P, bool need_field) {
+    if (!P) return fail(IRIS_ERR_INVALID, "params is NULL");
+    if (!P->emitter_of_face || !P->radiance || P->n_emitters <= 0 || !P->face_of_emitter || !P->emitter_vertices || !P->emitter_area ||
+        !P->emitter_pdf || !P->emitter_cdf)
+        return fail(IRIS_ERR_INVALID, "emitter tables missing");
+    if (!P->slf_inds || !P->slf_radiance || P->slf_H <= 0 || !(P->slf_range > 0.f)) return fail(IRIS_ERR_INVALID, "SLF tables missing");
+    if (need_field && (!P->grid_f16 || !P->mlp_f16 || !(P->field_range > 0.f))) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
+    return IRIS_OK;
+}
+
+int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roughness, const float *position, const float *normal, const float *wo,
+              int64_t n_pixels, int32_t spp, const IrisSampler *sampler, float *out0, float *out1, void *stream) {
+    if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
+    int rc = check_params(P, false);
+    if (rc) return rc;
+    if (n_pixels < 0 || spp <= 0 || !sampler) return fail(IRIS_ERR_INVALID, "bad bake arguments");
+    if (mode != 0 && mode != 1) return fail(IRIS_ERR_INVALID, "mode must be 0 (diffuse) or 1 (specular)");
+    if (n_pixels == 0) return IRIS_OK;
+    if (!position || !normal || !out0 || (mode == 1 && (!wo || !out1))) return fail(IRIS_ERR_INVALID, "NULL array");
+    if (sampler->U && sampler->stride < 2) return fail(IRIS_ERR_INVALID, "sampler stride < 2");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out0, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    if (mode == 1) CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    const int64_t n = n_pixels * spp;
+    if (mode == 0) k_bake<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
+    else k_bake<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+static int launch_field(const IrisShadeParams *P, int64_t n, const float *position, float *mat, const float4 *w0, float4 *w1, float4 *w2, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
+        attr_done = true;
+    }
+    const int64_t tiles = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 4);
+    if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+    else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t n, float *mat, void *stream) {
+    if (!P || !P->grid_f16 || !P->mlp_f16 || !(P->field_range > 0.f)) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
+    if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
+    if (n == 0) return IRIS_OK;
+    if (!position || !mat) return fail(IRIS_ERR_INVALID, "NULL array");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ensure_device_setup(dev);
+    if (rc) return rc;
+    return launch_field(P, n, position, mat, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int iris_field_backward(const IrisShadeParams *, const float *, const float *, int64_t, float *, void *) {
+    return fail(IRIS_ERR_INVALID, "iris_field_backward: not built yet");
+}
+
+int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {
+    const int64_t n = n_pixels * (int64_t)spp;
+    return 3 * 16 * n + 5 * 4 * n;   // w0,w1,w2 (forward) | d_mat (backward)
+}
+int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp) { return 6 * 16 * n_pixels * (int64_t)spp; }
+
+int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const float *rays, int64_t n_pixels, int32_t spp, const IrisSampler *sampler,
+                        float *L, void *record, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
+    int rc = check_params(P, true);
+    if (rc) return rc;
+    if (n_pixels < 0 || spp <= 0 || !sampler) return fail(IRIS_ERR_INVALID, "bad arguments");
+    if (n_pixels == 0) return IRIS_OK;
+    if (!rays || !L || !workspace) return fail(IRIS_ERR_INVALID, "NULL array");
+    if (sampler->U && sampler->stride < 8) return fail(IRIS_ERR_INVALID, "sampler stride < 8");
+    if (workspace_bytes < iris_single_workspace_bytes(n_pixels, spp)) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(record) & 15)) return fail(IRIS_ERR_INVALID, "workspace/record must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_pixels * spp;
+    float4 *w0 = reinterpret_cast<float4 *>(workspace), *w1 = w0 + n, *w2 = w1 + n;
+    CUDA_TRY(cudaMemsetAsync(L, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    k_primary<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1);
+    LAUNCHED();
+    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st);
+    if (rc) return rc;
+    if (record) k_bounce_single<true><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, reinterpret_cast<float4 *>(record));
+    else k_bounce_single<false><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, nullptr);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pixels, int32_t spp, const void *record, float *d_radiance,
+                         float *d_params, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!P) return fail(IRIS_ERR_INVALID, "params is NULL");
+    if (n_pixels < 0 || spp <= 0) return fail(IRIS_ERR_INVALID, "bad arguments");
+    if (n_pixels == 0) return IRIS_OK;
+    if (!dL || !record) return fail(IRIS_ERR_INVALID, "NULL array");
+    if (d_params) return fail(IRIS_ERR_INVALID, "BRDF-field adjoint: not built yet");
+    (void)workspace;
+    (void)workspace_bytes;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = P->n_emitters;
+    const size_t smem = K <= IRIS_BWD_KMAX ? (size_t)3 * K * IRIS_BLOCK * 4 : 0;
+    const int64_t n = n_pixels * spp;
+    const unsigned grid = (unsigned)std::min<int64_t>(blocks_for(n), (int64_t)g_sm_count * 8);
+    k_single_backward<<<grid, IRIS_BLOCK, smem, st>>>(dL, n_pixels, spp, reinterpret_cast<const float4 *>(record), K, d_radiance, nullptr);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// kernels.cuh -- the estimator kernels: ray cast, shading-map bake, path_tracing_single forward (primary + bounce) and its
+// replay adjoint.  One lane = one path sample; lane i belongs to pixel i / spp (the reference's repeat_interleave order,
+// utils/path_tracing.py:340).
+#pragma once
+#include "shading.cuh"
+
+
+
+// ------------------------------------------------------------------------------------------------ ray_intersect
+// utils/path_tracing.py:17-48
+__global__ void __launch_bounds__(IRIS_BLOCK) k_intersect(SceneView S, const float *__restrict__ o, const float *__restrict__ d, int64_t n,
+                                                           float *t, int32_t *prim, float *uv, float *p, float *nrm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 ro = ld3(o, i), rd = ld3(d, i);
+    const Hit h = trace_closest(S, ro, rd);
+    if (t) t[i] = h.t;
+    if (prim) prim[i] = h.prim;
+    if (uv) { uv[2 * i] = h.prim >= 0 ? h.u : 0.f; uv[2 * i + 1] = h.prim >= 0 ? h.v : 0.f; }
+    if (p || nrm) {
+        f3 hp, hn;
+        hit_surface(S, h, rd, hp, hn);
+        if (p) st3(p, i, hp);
+        if (nrm) st3(nrm, i, hn);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ per-pixel mean over spp
+// Lanes of one pixel are consecutive.  Segmented inclusive scan inside the warp, then the last lane of every segment
+// adds the segment sum (already scaled by 1/spp) to the pixel: one atomic per (warp, pixel) pair.
+__device__ __forceinline__ void pixel_accumulate(float *out, int64_t pixel, bool in_range, f3 v, float inv_spp) {
+    const unsigned lane = threadIdx.x & 31u;
+    const long long key = in_range ? (long long)pixel : -1 - (long long)lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float ux = __shfl_up_sync(0xffffffffu, v.x, o), uy = __shfl_up_sync(0xffffffffu, v.y, o), uz = __shfl_up_sync(0xffffffffu, v.z, o);
+        const long long uk = __shfl_up_sync(0xffffffffu, key, o);
+        if (lane >= (unsigned)o && uk == key) { v.x += ux; v.y += uy; v.z += uz; }
+    }
+    const long long nk = __shfl_down_sync(0xffffffffu, key, 1);
+    if (in_range && (lane == 31u || nk != key)) {
+        atomicAdd(out + 3 * pixel, v.x * inv_spp);
+        atomicAdd(out + 3 * pixel + 1, v.y * inv_spp);
+        atomicAdd(out + 3 * pixel + 2, v.z * inv_spp);
+    }
+}
+
+// Radiance seen along a secondary ray when every non-emissive hit terminates in the SLF (trace_roughness == 0:
+// bake_shading.py:121-122 and path_tracing_single, utils/path_tracing.py:395).  model/emitter.py:180-221.
+// e_hit: emitter row if the hit triangle is an emitter, else -1.  valid_next as the reference defines it.
+__device__ __forceinline__ f3 radiance_at_hit(const IrisShadeParams &P, const Hit &h, f3 p, int32_t &e_hit, float &emit_pdf, bool &valid_next) {
+    e_hit = emitter_of(P, h.prim);
+    emit_pdf = 0.f;
+    valid_next = false;
+    if (h.prim < 0) return mk3(0.f, 0.f, 0.f);
+    if (e_hit >= 0) { emit_pdf = emitter_pdf_area(P, e_hit); return emitter_radiance(P, e_hit); }
+    const f3 S = slf_lookup(P, p);
+    valid_next = !(S.x + S.y + S.z > 0.f);
+    return S;
+}
+
+// ------------------------------------------------------------------------------------------------ bake
+// bake_shading.py:108-123 (MODE 0) and :168-188 (MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_bake(SceneView S, IrisShadeParams P, IrisSampler smp, float roughness,
+                                                      const float *__restrict__ position, const float *__restrict__ normal,
+                                                      const float *__restrict__ wo_in, int64_t n_pixels, int spp, float *out0, float *out1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = n_pixels * spp;
+    const bool in_range = i < n;
+    const int64_t pix = in_range ? i / spp : 0;
+    f3 L0 = mk3(0.f, 0.f, 0.f), L1 = mk3(0.f, 0.f, 0.f);
+    if (in_range) {
+        const f3 x = ld3(position, pix), nr = ld3(normal, pix);
+        const float4 u = sample4(smp, i, 0);
+        f3 wi;
+        float w0 = 1.f, w1 = 0.f;
+        if (MODE == 0) {
+            wi = diffuse_sampler(u.x, u.y, nr);
+        } else {
+            const f3 wo = ld3(wo_in, pix);
+            wi = specular_sampler(u.x, u.y, roughness, wo, nr);
+            specular_weights(wi, wo, nr, roughness, w0, w1);
+        }
+        const f3 org = mk3(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z);
+        const Hit h = trace_closest(S, org, wi);
+        f3 hp, hn;
+        hit_surface(S, h, wi, hp, hn);
+        int32_t e;
+        float epdf;
+        bool vn;
+        const f3 Le = radiance_at_hit(P, h, hp, e, epdf, vn);
+        L0 = Le * w0;
+        L1 = Le * w1;
+    }
+    const float inv = 1.f / (float)spp;
+    pixel_accumulate(out0, pix, in_range, L0, inv);
+    if (MODE == 1) pixel_accumulate(out1, pix, in_range, L1, inv);
+}
+
+// ------------------------------------------------------------------------------------------------ path_tracing_single
+// Workspace per lane: three float4.
+//   w0 = (x0.xyz, code)   code: -2 = continue (valid_next), -1 = miss, >= 0 = emitter row hit by the primary ray
+//   w1 = (n0.xyz, metallic)        w2 = (albedo.rgb, roughness)      [w1.w, w2 written by the field kernel]
+__device__ __forceinline__ f3 camera_dir(const float *__restrict__ rays, int64_t pix, float u0, float u1) {
+    // utils/path_tracing.py:338-339, one rounding per op like the ATen chain
+    const float *r = rays + 12 * pix;
+    const float du = xsub(u0, 0.5f), dv = xsub(u1, 0.5f);
+    const f3 v = mk3(xadd(xadd(r[3], xmul(r[6], du)), xmul(r[9], dv)), xadd(xadd(r[4], xmul(r[7], du)), xmul(r[10], dv)),
+                     xadd(xadd(r[5], xmul(r[8], du)), xmul(r[11], dv)));
+    const float l = fmaxf(__fsqrt_rn(xadd(xadd(xmul(v.x, v.x), xmul(v.y, v.y)), xmul(v.z, v.z))), 1e-12f);
+    return mk3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
+}
+
+__global__ void __launch_bounds__(IRIS_BLOCK) k_primary(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
+                                                         int64_t n_pixels, int spp, float4 *__restrict__ w0, float4 *__restrict__ w1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels * spp) return;
+    const int64_t pix = i / spp;
+    const float4 u = sample4(smp, i, 0);
+    const f3 o = mk3(rays[12 * pix], rays[12 * pix + 1], rays[12 * pix + 2]);
+    const f3 wi = camera_dir(rays, pix, u.x, u.y);
+    const Hit h = trace_closest(S, o, wi);
+    f3 hp, hn;
+    hit_surface(S, h, wi, hp, hn);
+    int code = -1;
+    if (h.prim >= 0) {
+        const int32_t e = emitter_of(P, h.prim);
+        code = e >= 0 ? e : -2;
+    }
+    w0[i] = make_float4(hp.x, hp.y, hp.z, __int_as_float(code));
+    w1[i] = make_float4(hn.x, hn.y, hn.z, 0.f);
+}
+
+// Backward record per lane: six float4 (SoA by word so that lanes coalesce).
+//   r0 = (e0, e_nee, e_b, -)        emitter rows of the three radiance gathers (-1 = none), as int bits
+//   r1 = (c_nee.xyz, c_b.x)         dL/dradiance[e_nee] = g * c_nee,  dL/dradiance[e_b] = g * c_b,  dL/dradiance[e0] = g
+//   r2 = (c_b.yz, Ja.xy)   r3 = (Ja.z, Jr.xyz)   r4 = (Jm.xyz, -)     J* = d(L_c)/d(albedo_c | roughness | metallic)
+//   r5 = (x0.xyz, code)
+template <bool RECORD>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_bounce_single(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
+                                                               int64_t n_pixels, int spp, const float4 *__restrict__ w0,
+                                                               const float4 *__restrict__ w1, const float4 *__restrict__ w2, float *L_out,
+                                                               float4 *__restrict__ rec) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = n_pixels * spp;
+    const bool in_range = i < n;
+    const int64_t pix = in_range ? i / spp : 0;
+    f3 L = mk3(0.f, 0.f, 0.f);
+    if (in_range) {
+        const float4 a = w0[i];
+        const int code = __float_as_int(a.w);
+        int32_t e0 = -1, e_nee = -1, e_b = -1;
+        f3 c_nee = mk3(0.f, 0.f, 0.f), c_b = mk3(0.f, 0.f, 0.f);
+        f3 Ja = c_nee, Jr = c_nee, Jm = c_nee;
+        if (code >= 0) {
+            e0 = code;
+            L = emitter_radiance(P, e0);
+        } else if (code == -2) {
+            const float4 b = w1[i], c = w2[i];
+            const f3 x0 = mk3(a.x, a.y, a.z), n0 = mk3(b.x, b.y, b.z);
+            Mat mat;
+            mat.a = mk3(c.x, c.y, c.z);
+            mat.r = c.w;
+            mat.m = b.w;
+            const float4 ua = sample4(smp, i, 0), ub = sample4(smp, i, 1);
+            const f3 wo = -camera_dir(rays, pix, ua.x, ua.y);
+            // ---- emitter sampling + shadow ray + MIS (utils/path_tracing.py:359-382)
+            {
+                f3 wi;
+                float pdf_e;
+                int32_t e, face;
+                sample_emitter(P, ua.z, ua.w, ub.x, x0, wi, pdf_e, e, face);
+                const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+                const Hit h = trace_closest(S, org, wi);
+                f3 hp, hn;
+                hit_surface(S, h, wi, hp, hn);
+                const bool hit = h.prim >= 0;
+                const bool vis = !hit || h.prim == face;
+                const int32_t eh = emitter_of(P, h.prim);
+                float G = 1.f;
+                if (hit) {
+                    const f3 dlt = hp - x0;
+                    G = fabsf(-(wi.x * hn.x) - (wi.y * hn.y) - (wi.z * hn.z)) / fmaxf(dot(dlt, dlt), 1e-6f);
+                }
+                f3 f;
+                float pdf_b;
+                BrdfJac J;
+                eval_brdf<RECORD>(wi, wo, n0, mat, f, pdf_b, &J);
+                pdf_b *= G;
+                float w = (pdf_e > 0.f && !isinf(pdf_b)) ? pdf_e * pdf_e / fmaxf(pdf_e * pdf_e + pdf_b * pdf_b, 1e-6f) : 0.f;
+                if (isinf(pdf_e) || pdf_b == 0.f) w = 1.f;
+                const float s = (vis ? 1.f : 0.f) * G / fmaxf(pdf_e, 1e-6f) * w;
+                if (hit && eh >= 0) {
+                    const f3 Le = emitter_radiance(P, eh);
+                    const f3 W = Le * s;
+                    L = L + f * W;
+                    if (RECORD) {
+                        if (vis) { e_nee = eh; c_nee = f * s; }
+                        Ja = Ja + J.da * W; Jr = Jr + J.dr * W; Jm = Jm + J.dm * W;
+                    }
+                }
+            }
+            // ---- BSDF sampling + ray + emitter / SLF radiance + MIS (utils/path_tracing.py:385-404)
+            {
+                f3 wi, wb;
+                float pdf_b;
+                BrdfJac J;
+                sample_brdf<RECORD>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
+                const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+                const Hit h = trace_closest(S, org, wi);
+                f3 hp, hn;
+                hit_surface(S, h, wi, hp, hn);
+                int32_t eh;
+                float pdf_e;
+                bool vn;
+                const f3 Le = radiance_at_hit(P, h, hp, eh, pdf_e, vn);
+                float G = 1.f;
+                if (vn) {
+                    const f3 dlt = x0 - hp;
+                    G = fabsf(-(hn.x * wi.x) - (hn.y * wi.y) - (hn.z * wi.z)) / fmaxf(dot(dlt, dlt), 1e-6f);
+                }
+                pdf_b *= G;
+                float w = (pdf_b > 0.f && !isinf(pdf_e)) ? pdf_b * pdf_b / (pdf_e * pdf_e + pdf_b * pdf_b) : 0.f;
+                if (isinf(pdf_b) || pdf_e == 0.f) w = 1.f;
+                L = L + wb * Le * w;
+                if (RECORD) {
+                    if (eh >= 0) { e_b = eh; c_b = wb * w; }
+                    const f3 Lw = Le * w;
+                    Ja = Ja + J.da * Lw; Jr = Jr + J.dr * Lw; Jm = Jm + J.dm * Lw;
+                }
+            }
+        }
+        if (RECORD) {
+            rec[i] = make_float4(__int_as_float(e0), __int_as_float(e_nee), __int_as_float(e_b), 0.f);
+            rec[n + i] = make_float4(c_nee.x, c_nee.y, c_nee.z, c_b.x);
+            rec[2 * n + i] = make_float4(c_b.y, c_b.z, Ja.x, Ja.y);
+            rec[3 * n + i] = make_float4(Ja.z, Jr.x, Jr.y, Jr.z);
+            rec[4 * n + i] = make_float4(Jm.x, Jm.y, Jm.z, 0.f);
+            rec[5 * n + i] = a;
+        }
+    }
+    pixel_accumulate(L_out, pix, in_range, L, 1.f / (float)spp);
+}
+
+// ------------------------------------------------------------------------------------------------ adjoint
+// Replays the record: g = dL[pixel]/spp per lane.  Emitter-radiance gradients are reduced in per-thread shared-memory
+// accumulators over a grid-stride loop (no atomics, no bank conflicts), then across the block, and leave the block as
+// ONE atomic per emitter row and channel.  d_mat (n,5) = J^T g feeds the field adjoint.
+#define IRIS_BWD_KMAX 96   // 96 rows * 3 * 128 threads * 4 B = 147 KB dynamic shared memory
+__global__ void __launch_bounds__(IRIS_BLOCK) k_single_backward(const float *__restrict__ dL, int64_t n_pixels, int spp,
+                                                                 const float4 *__restrict__ rec, int K, float *d_radiance, float *d_mat) {
+    extern __shared__ float acc[];   // [K*3][IRIS_BLOCK] when K <= IRIS_BWD_KMAX
+    const bool priv = K <= IRIS_BWD_KMAX;
+    const int tid = threadIdx.x;
+    if (priv)
+        for (int r = 0; r < 3 * K; ++r) acc[r * IRIS_BLOCK + tid] = 0.f;
+    const int64_t n = n_pixels * spp;
+    const float inv = 1.f / (float)spp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i / spp;
+        const f3 g = mk3(dL[3 * pix] * inv, dL[3 * pix + 1] * inv, dL[3 * pix + 2] * inv);
+        const float4 r0 = rec[i], r1 = rec[n + i], r2 = rec[2 * n + i];
+        const int e0 = __float_as_int(r0.x), en = __float_as_int(r0.y), eb = __float_as_int(r0.z);
+        if (d_radiance) {
+            if (priv) {
+                if (e0 >= 0) { acc[(3 * e0) * IRIS_BLOCK + tid] += g.x; acc[(3 * e0 + 1) * IRIS_BLOCK + tid] += g.y; acc[(3 * e0 + 2) * IRIS_BLOCK + tid] += g.z; }
+                if (en >= 0) { acc[(3 * en) * IRIS_BLOCK + tid] += g.x * r1.x; acc[(3 * en + 1) * IRIS_BLOCK + tid] += g.y * r1.y; acc[(3 * en + 2) * IRIS_BLOCK + tid] += g.z * r1.z; }
+                if (eb >= 0) { acc[(3 * eb) * IRIS_BLOCK + tid] += g.x * r1.w; acc[(3 * eb + 1) * IRIS_BLOCK + tid] += g.y * r2.x; acc[(3 * eb + 2) * IRIS_BLOCK + tid] += g.z * r2.y; }
+            } else {
+                if (e0 >= 0) { atomicAdd(d_radiance + 3 * e0, g.x); atomicAdd(d_radiance + 3 * e0 + 1, g.y); atomicAdd(d_radiance + 3 * e0 + 2, g.z); }
+                if (en >= 0) { atomicAdd(d_radiance + 3 * en, g.x * r1.x); atomicAdd(d_radiance + 3 * en + 1, g.y * r1.y); atomicAdd(d_radiance + 3 * en + 2, g.z * r1.z); }
+                if (eb >= 0) { atomicAdd(d_radiance + 3 * eb, g.x * r1.w); atomicAdd(d_radiance + 3 * eb + 1, g.y * r2.x); atomicAdd(d_radiance + 3 * eb + 2, g.z * r2.y); }
+            }
+        }
+        if (d_mat) {
+            const float4 r3 = rec[3 * n + i], r4 = rec[4 * n + i];
+            float *o = d_mat + 5 * i;
+            o[0] = g.x * r2.z;
+            o[1] = g.y * r2.w;
+            o[2] = g.z * r3.x;
+            o[3] = g.x * r3.y + g.y * r3.z + g.z * r3.w;
+            o[4] = g.x * r4.x + g.y * r4.y + g.z * r4.z;
+        }
+    }
+    if (priv && d_radiance) {
+        __syncthreads();
+        // row r is reduced by warp (r % 4): 128 partials -> 1
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < 3 * K; r += IRIS_BLOCK / 32) {
+            float v = acc[r * IRIS_BLOCK + lane] + acc[r * IRIS_BLOCK + lane + 32] + acc[r * IRIS_BLOCK + lane + 64] + acc[r * IRIS_BLOCK + lane + 96];
+            v = warp_sum(v);
+            if (lane == 0 && v != 0.f) atomicAdd(d_radiance + r, v);
+        }
+    }
+}

@@ -1,0 +1,175 @@
+// traverse.cuh -- closest-hit traversal of the 8-wide compressed BVH (bvh8.h) + the exact triangle test.
+//
+// Replaces scene.ray_intersect_preliminary (OptiX) behind ray_intersect, reference utils/path_tracing.py:30-35.
+// One ray per lane.  Per visited node the lane issues five 16-byte read-only loads (the whole 80-byte node), decodes
+// eight quantised child boxes with byte arithmetic, and keeps (node group, triangle group) bit masks so that the
+// traversal stack holds at most one 8-byte entry per level (Ylitie, Karras, Laine 2017).  Hit selection is the
+// oracle's: minimum t, ties to the lowest prim index; box tests use `<=` so equal-t triangles are never culled.
+#pragma once
+#include "bvh8.h"
+#include "common.cuh"
+
+#define IRIS_STACK 32
+
+struct SceneView {
+    const float4 *nodes;   // 5 per node
+    const float4 *tris;    // 3 per triangle record
+    int64_t n_tris;
+};
+
+struct Hit {
+    float t, u, v;
+    int32_t prim;   // caller's face index, -1 = miss
+    int32_t slot;   // record index in SceneView::tris
+};
+
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+#ifdef IRIS_HOST_EMULATION   // tests/host/traverse_host.cpp
+    return ((x >> 7) & 0x01010101u) * 0xFFu;
+#else
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+
+// Moller-Trumbore barycentrics + projected t, operation order of oracle/intersect.c:tri_test (rdd = 1/(d.d))
+__device__ __forceinline__ bool tri_test(f3 o, f3 d, float rdd, f3 v0, f3 e1, f3 e2, float &t, float &u, float &v) {
+    f3 p = xcross(d, e2);
+    float det = xdot(e1, p);
+    float mag = xadd(xadd(fabsf(xmul(e1.x, p.x)), fabsf(xmul(e1.y, p.y))), fabsf(xmul(e1.z, p.z)));
+    if (!(fabsf(det) > xmul(1e-6f, mag))) return false;
+    float inv = __fdiv_rn(1.0f, det);
+    f3 s = mk3(xsub(o.x, v0.x), xsub(o.y, v0.y), xsub(o.z, v0.z));
+    float uu = xmul(xdot(s, p), inv);
+    if (!(uu >= 0.0f && uu <= 1.0f)) return false;
+    f3 q = xcross(s, e1);
+    float vv = xmul(xdot(d, q), inv);
+    if (!(vv >= 0.0f && xadd(uu, vv) <= 1.0f)) return false;
+    f3 h = mk3(xsub(__fmaf_rn(vv, e2.x, __fmaf_rn(uu, e1.x, v0.x)), o.x), xsub(__fmaf_rn(vv, e2.y, __fmaf_rn(uu, e1.y, v0.y)), o.y),
+               xsub(__fmaf_rn(vv, e2.z, __fmaf_rn(uu, e1.z, v0.z)), o.z));
+    float tt = xmul(xdot(h, d), rdd);
+    if (!(tt > 0.0f && tt < __int_as_float(0x7f800000))) return false;
+    t = tt; u = uu; v = vv;
+    return true;
+}
+
+__device__ __forceinline__ void load_tri(const SceneView &S, int32_t slot, f3 &v0, f3 &e1, f3 &e2, int32_t &prim) {
+    const float4 a = ldg4(S.tris + 3 * (int64_t)slot), b = ldg4(S.tris + 3 * (int64_t)slot + 1), c = ldg4(S.tris + 3 * (int64_t)slot + 2);
+    v0 = mk3(a.x, a.y, a.z);
+    e1 = mk3(a.w, b.x, b.y);
+    e2 = mk3(b.z, b.w, c.x);
+    prim = __float_as_int(c.y);
+}
+
+__device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
+    Hit best;
+    best.t = __int_as_float(0x7f800000);
+    best.u = best.v = 0.f;
+    best.prim = -1;
+    best.slot = -1;
+
+    uint2 stack[IRIS_STACK];
+    int sp = 0;
+
+    const float sx = fabsf(d.x) < 1e-30f ? copysignf(1e-30f, d.x) : d.x;
+    const float sy = fabsf(d.y) < 1e-30f ? copysignf(1e-30f, d.y) : d.y;
+    const float sz = fabsf(d.z) < 1e-30f ? copysignf(1e-30f, d.z) : d.z;
+    const float idx = 1.0f / sx, idy = 1.0f / sy, idz = 1.0f / sz;
+    const uint32_t octinv = (sx < 0.f ? 0u : 4u) | (sy < 0.f ? 0u : 2u) | (sz < 0.f ? 0u : 1u);
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    const float rdd = __fdiv_rn(1.0f, xdot(d, d));
+
+    uint2 ngroup = make_uint2(0u, 0x80000000u);
+    uint2 tgroup = make_uint2(0u, 0u);
+
+    while (true) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t hits = ngroup.y;
+            const uint32_t imask = ngroup.y;
+            const uint32_t bit = 31u - __clz(hits);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00FFFFFFu) {
+                stack[sp++] = ngroup;   // depth <= IRIS_STACK is checked when the scene is built
+            }
+            const uint32_t slot = (bit - 24u) ^ octinv;
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+            const float4 *np = S.nodes + 5 * (int64_t)(base + rel);
+            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
+            const uint32_t ew = __float_as_uint(n0.w);
+            ngroup.x = __float_as_uint(n1.x);
+            tgroup.x = __float_as_uint(n1.y);
+            const float ax = __uint_as_float((ew & 0xFFu) << 23) * idx;
+            const float ay = __uint_as_float(((ew >> 8) & 0xFFu) << 23) * idy;
+            const float az = __uint_as_float(((ew >> 16) & 0xFFu) << 23) * idz;
+            const float bx = (n0.x - o.x) * idx, by = (n0.y - o.y) * idy, bz = (n0.z - o.z) * idz;
+            uint32_t hitmask = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
+                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+                const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlx = __float_as_uint(h ? n2.y : n2.x), qly = __float_as_uint(h ? n2.w : n2.z), qlz = __float_as_uint(h ? n3.y : n3.x);
+                const uint32_t qhx = __float_as_uint(h ? n3.w : n3.z), qhy = __float_as_uint(h ? n4.y : n4.x), qhz = __float_as_uint(h ? n4.w : n4.z);
+                const uint32_t nx = sx < 0.f ? qhx : qlx, fx = sx < 0.f ? qlx : qhx;
+                const uint32_t ny = sy < 0.f ? qhy : qly, fy = sy < 0.f ? qly : qhy;
+                const uint32_t nz = sz < 0.f ? qhz : qlz, fz = sz < 0.f ? qlz : qhz;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
+                    const float t0y = fmaf(byte_f(ny, j), ay, by), t1y = fmaf(byte_f(fy, j), ay, by);
+                    const float t0z = fmaf(byte_f(nz, j), az, bz), t1z = fmaf(byte_f(fz, j), az, bz);
+                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best.t));
+                    if (tn <= tf) {
+                        const uint32_t cb = (child_bits4 >> (8 * j)) & 0xFFu;
+                        const uint32_t bi = (bit_index4 >> (8 * j)) & 0xFFu;
+                        hitmask |= cb << bi;
+                    }
+                }
+            }
+            ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
+            tgroup.y = hitmask & 0x00FFFFFFu;
+        } else {
+            tgroup = ngroup;
+            ngroup = make_uint2(0u, 0u);
+        }
+        while (tgroup.y != 0u) {
+            const uint32_t ti = 31u - __clz(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const int32_t slot = (int32_t)(tgroup.x + ti);
+            f3 v0, e1, e2;
+            int32_t prim;
+            load_tri(S, slot, v0, e1, e2, prim);
+            float t, u, v;
+            if (tri_test(o, d, rdd, v0, e1, e2, t, u, v)) {
+                if (t < best.t || (t == best.t && prim < best.prim)) {
+                    best.t = t; best.u = u; best.v = v; best.prim = prim; best.slot = slot;
+                }
+            }
+        }
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            ngroup = stack[--sp];
+        }
+    }
+    return best;
+}
+
+// Surface record of a hit: p = fma(v,e2,fma(u,e1,v0)), n = normalize(e1 x e2) flipped toward -d (oracle finish()).
+__device__ __forceinline__ void hit_surface(const SceneView &S, const Hit &h, f3 d, f3 &p, f3 &n) {
+    if (h.prim < 0) { p = mk3(0.f, 0.f, 0.f); n = mk3(0.f, 0.f, 0.f); return; }
+    f3 v0, e1, e2;
+    int32_t prim;
+    load_tri(S, h.slot, v0, e1, e2, prim);
+    p = mk3(__fmaf_rn(h.v, e2.x, __fmaf_rn(h.u, e1.x, v0.x)), __fmaf_rn(h.v, e2.y, __fmaf_rn(h.u, e1.y, v0.y)),
+            __fmaf_rn(h.v, e2.z, __fmaf_rn(h.u, e1.z, v0.z)));
+    f3 c = xcross(e1, e2);
+    float len = __fsqrt_rn(xdot(c, c));
+    n = mk3(__fdiv_rn(c.x, len), __fdiv_rn(c.y, len), __fdiv_rn(c.z, len));
+    if (xdot(n, d) > 0.0f) n = -n;
+}

@@ -15,7 +15,7 @@ vector for it.  The contract is self-consistency: the CUD
 iris_b200/csrc/field.cu must match THIS file, rounding points included.
 
 Definitions (every item "tcnn-1.7-compatible by construction, unverified"):
-  level l:  scale_l = 16 * 1.3^l - 1   (exp2f(l*log2f(1.3f))*16 - 1 in fp32)
+  level l:  scale_l = fp32(16 * (double)1.3f ^ l - 1)   (evaluated in float64, rounded once)
             res_l   = ceil(scale_l) + 1
             size_l  = min(next_multiple(res_l^3, 8), 2^19)      entries of 2 features
   lookup:   pos = fmaf(scale_l, x, 0.5); cell = floor(pos); w = pos - cell;
@@ -54,9 +54,11 @@ PRIME_Z = 805459861
 def level_table():
     """(scale fp32, res, size, offset-in-entries) per level and the total entry count."""
     out, off = [], 0
-    l2 = np.float32(np.log2(np.float32(PER_LEVEL_SCALE)))
+    base = float(np.float32(PER_LEVEL_SCALE))
     for l in range(N_LEVELS):
-        scale = np.float32(np.exp2(np.float32(l) * l2) * np.float32(BASE_RES) - np.float32(1.0))
+        # tcnn evaluates exp2f(l*log2f(1.3f))*16-1 whose last bits depend on the libm at hand; the restatement pins the
+        # value portably: the same expression in float64, rounded once to fp32
+        scale = np.float32(float(BASE_RES) * math.pow(base, l) - 1.0)
         res = int(math.ceil(float(scale))) + 1
         dense = res ** 3
         size = min(dense, (2 ** 32 - 1) // 2)

@@ -9,13 +9,18 @@
  * with OptiX itself is unpinned:
  *
  *   - exact closest hit over all triangles of one mesh, prim index = face order;
- *   - Moller-Trumbore in fp32, one rounding per operation (compile with
+ *   - Moller-Trumbore barycentrics in fp32, one rounding per operation (compile with
  *     -ffp-contract=off), fixed operation order shared bit-for-bit with the CUDA kernel
- *     (iris_b200/csrc/tri_test.cuh);
- *   - hit iff det != 0, 0<=u<=1, v>=0, u+v<=1, 0 < t < inf; equal t -> lowest prim index,
- *     and the ray is flagged in `tie`;
- *   - p = fma(v,e2,fma(u,e1,v0)) (barycentric interpolation), n = normalize(e1 x e2)
- *     flipped so that dot(n,-d) >= 0 (utils/ops.py:85-96), uv = (u,v);
+ *     (iris_b200/csrc/traverse.cuh:tri_test);
+ *   - det = e1.(d x e2) must clear a noise floor: |det| > 1e-6 * (|e1x px|+|e1y py|+|e1z pz|)
+ *     (rays within ~1e-6 rad of the triangle's plane count as parallel); triangles whose
+ *     e1 x e2 is exactly zero never hit;
+ *   - hit iff 0<=u<=1, v>=0, u+v<=1, 0 < t < inf where p = fma(v,e2,fma(u,e1,v0)) is the
+ *     barycentric point and t = ((p-o).d) * (1/(d.d)) its projection on the ray -- unlike
+ *     Moller-Trumbore's own t this stays well conditioned at grazing angles, so the hit always
+ *     lies inside the triangle's bounding box and BVH culling agrees with the brute-force loop;
+ *   - equal t -> lowest prim index, and the ray is flagged in `tie`;
+ *   - n = normalize(e1 x e2) flipped so that dot(n,-d) >= 0 (utils/ops.py:85-96), uv = (u,v);
  *   - miss -> t=inf, prim=-1, p=n=uv=0.
  *
  * Two drivers share the triangle test: a brute-force loop (ground truth for small
@@ -37,13 +42,14 @@ static inline void cross3(const float a[3], const float b[3], float r[3])
     r[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-/* returns 1 on hit and writes t,u,v */
-static inline int tri_test(const float o[3], const float d[3], const Tri *tr, float *t, float *u, float *v)
+/* returns 1 on hit and writes t,u,v; rdd = 1/(d.d) */
+static inline int tri_test(const float o[3], const float d[3], float rdd, const Tri *tr, float *t, float *u, float *v)
 {
     float p[3], s[3], q[3];
     cross3(d, tr->e2, p);
     float det = dot3(tr->e1, p);
-    if (det == 0.0f) return 0;
+    float mag = (fabsf(tr->e1[0] * p[0]) + fabsf(tr->e1[1] * p[1])) + fabsf(tr->e1[2] * p[2]);
+    if (!(fabsf(det) > 1e-6f * mag)) return 0;
     float inv = 1.0f / det;
     s[0] = o[0] - tr->v0[0]; s[1] = o[1] - tr->v0[1]; s[2] = o[2] - tr->v0[2];
     float uu = dot3(s, p) * inv;
@@ -51,7 +57,9 @@ static inline int tri_test(const float o[3], const float d[3], const Tri *tr, fl
     cross3(s, tr->e1, q);
     float vv = dot3(d, q) * inv;
     if (!(vv >= 0.0f && uu + vv <= 1.0f)) return 0;
-    float tt = dot3(tr->e2, q) * inv;
+    float h[3];
+    for (int k = 0; k < 3; ++k) h[k] = fmaf(vv, tr->e2[k], fmaf(uu, tr->e1[k], tr->v0[k])) - o[k];
+    float tt = dot3(h, d) * rdd;
     if (!(tt > 0.0f && tt < INFINITY)) return 0;
     *t = tt; *u = uu; *v = vv;
     return 1;
@@ -133,6 +141,10 @@ OracleScene *oracle_scene_create(const float *verts, int64_t nv, const int32_t *
             ghi = fmaxf(ghi, fmaxf(a[k], fmaxf(b[k], c[k])));
         }
         S->order[f] = (int32_t)f;
+        float cr[3];
+        cross3(S->tris[f].e1, S->tris[f].e2, cr);
+        if (cr[0] == 0.0f && cr[1] == 0.0f && cr[2] == 0.0f)      /* zero-area triangle: never hit */
+            for (int k = 0; k < 3; ++k) S->tris[f].e1[k] = S->tris[f].e2[k] = 0.0f;
     }
     S->pad = nf > 0 ? 1e-5f * (ghi - glo) + 1e-30f : 0.0f;
     S->n_nodes = 1;
@@ -147,11 +159,11 @@ void oracle_scene_destroy(OracleScene *S)
     free(S->tris); free(S->order); free(S->nodes); free(S);
 }
 
-static inline void consider(const OracleScene *S, int32_t f, const float o[3], const float d[3],
+static inline void consider(const OracleScene *S, int32_t f, const float o[3], const float d[3], float rdd,
                             float *bt, int32_t *bp, float *bu, float *bv, uint8_t *tie)
 {
     float t, u, v;
-    if (!tri_test(o, d, &S->tris[f], &t, &u, &v)) return;
+    if (!tri_test(o, d, rdd, &S->tris[f], &t, &u, &v)) return;
     if (t < *bt) { *bt = t; *bp = f; *bu = u; *bv = v; *tie = 0; }
     else if (t == *bt) { *tie = 1; if (f < *bp) { *bp = f; *bu = u; *bv = v; } }
 }
@@ -187,8 +199,9 @@ void oracle_intersect(const OracleScene *S, int mode, const float *os, const flo
         float bt = INFINITY, bu = 0, bv = 0;
         int32_t bp = -1;
         uint8_t tflag = 0;
+        const float rdd = 1.0f / dot3(d, d);
         if (mode == 0 || S->nf == 0) {
-            for (int64_t f = 0; f < S->nf; ++f) consider(S, (int32_t)f, o, d, &bt, &bp, &bu, &bv, &tflag);
+            for (int64_t f = 0; f < S->nf; ++f) consider(S, (int32_t)f, o, d, rdd, &bt, &bp, &bu, &bv, &tflag);
         } else {
             float id[3];
             for (int k = 0; k < 3; ++k) {
@@ -212,7 +225,7 @@ void oracle_intersect(const OracleScene *S, int mode, const float *os, const flo
                 if (tn > tf) continue;
                 if (nd->count > 0) {
                     for (int32_t i = nd->left; i < nd->left + nd->count; ++i)
-                        consider(S, S->order[i], o, d, &bt, &bp, &bu, &bv, &tflag);
+                        consider(S, S->order[i], o, d, rdd, &bt, &bp, &bu, &bv, &tflag);
                 } else {
                     if (sp + 2 > 256) abort();
                     stack[sp++] = nd->left;
