@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- path samples / second, forward + backward, for the differentiable shading hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A *step* = one pass of `path_tracing_single` forward + adjoint over one batch of synthetic camera rays:
+workload "c4" (default; BASELINE.json configs[3], the train_emitter.py step): 1M-triangle room, 8 views 1280x960 per GPU,
+SPP=256 as 8 chunks of spp=32, K=16 emitter triangles, MIS on, MSE loss, gradient to emitter.radiance; the scene/BVH, SLF and
+BRDF field are replicated, pixels are sharded by view, and the only collective is the allreduce of d_radiance.
+A *path sample* = one (pixel, spp index) lane through the whole estimator (3 ray casts, BRDF-field evaluation, emitter / SLF
+lookups, MIS, adjoint replay).
+
+Prints ONE JSON line (rank 0).  `value` times the steps with inputs resident in HBM; `e2e` times the same steps through the
+public API with the rays in pinned HOST memory (H2D inside the timed region, loss + gradient read back).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: tris, emitters, views per GPU, width, height, SPP, spp, estimator
+    "c4": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32,
+               desc="train_emitter step: path_tracing_single fwd+bwd, emitter-radiance gradient, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), K=16, MIS on"),
+    "c1": dict(tris=10_000, emitters=2, views=1, width=64, height=64, SPP=16, spp=16,
+               desc="Cornell ~10k tris, 64x64, spp=16, path_tracing_single fwd+bwd (reference's CPU-runnable case)"),
+}
+
+
+def ray_bytes(n_tris):
+    """one root-to-leaf path of an 8-wide 80-byte BVH + one 48-byte triangle."""
+    return math.ceil(math.log(max(n_tris, 8) / 4.0, 8)) * 80 + 48
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--views", type=int, default=None)
+    ap.add_argument("--tile", type=int, default=262144, help="pixels per forward/backward tile")
+    ap.add_argument("--cpu-sample-pixels", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_leg(w, sc, n_pixels, steps, warmup):
+    """The reference's own algorithm for this path on the host cores: oracle/estimators.path_tracing_single forward + autograd
+    backward to emitter radiance, on the first n_pixels pixels of view 0 with spp = w['spp'] (one chunk)."""
+    import torch
+    from oracle import estimators as E
+    from oracle import field as OF
+    from oracle.intersect import OracleScene
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    osc = OracleScene(sc.vertices, sc.faces)
+    em = E.Emitter(sc.emitter_dict(), sc.slf_dict(256), learn=True)
+    params = bench_params()
+    vmin, vmax = sc.voxel_bounds()
+    mat_fn = lambda x: OF.material(x, params, vmin, vmax)
+    rays = torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=1))
+    stride = max(1, len(rays) // n_pixels)
+    r = rays[::stride][:n_pixels]
+    spp = w["spp"]
+    rng = np.random.default_rng(0)
+    times = []
+    for it in range(warmup + steps):
+        U = torch.as_tensor(np.minimum(rng.random((len(r) * spp, 8), dtype=np.float32), np.float32(0.99999)))
+        t0 = time.perf_counter()
+        L = E.path_tracing_single(osc, em, mat_fn, r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], spp, U)
+        loss = ((L - 0.5) ** 2).mean()
+        em.radiance.grad = None
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per = float(np.mean(times))
+    return dict(value=len(r) * spp / per, unit="samples/s", cores=cores, kind="port",
+                sample="%d pixels (every %d-th of view 1) x spp %d, one chunk, fwd+bwd to emitter.radiance" % (len(r), stride, spp)), per
+
+
+def bench_params():
+    """Random-init BRDF field: tcnn-style grid U(+-1e-4) + Xavier MLP."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    p = torch.empty(9216 + 27954112)
+    b = math.sqrt(6.0 / 128)
+    p[:8192] = (torch.rand(8192, generator=g) * 2 - 1) * b
+    p[8192:9216] = (torch.rand(1024, generator=g) * 2 - 1) * math.sqrt(6.0 / 80)
+    p[9216:] = (torch.rand(27954112, generator=g) * 2 - 1) * 1e-4
+    return p
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    a = parse()
+    w = dict(WORKLOADS[a.workload])
+    if a.views:
+        w["views"] = a.views
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from iris_b200 import scenes
+    n_chunks = w["SPP"] // w["spp"]
+    pix_per_view = w["width"] * w["height"]
+    config = dict(workload=a.workload, description=w["desc"], triangles=None, views_per_gpu=w["views"], width=w["width"], height=w["height"],
+                  SPP=w["SPP"], spp=w["spp"], emitters=w["emitters"], slf_H=256, sharding="pixels by view, scene/SLF/field replicated, allreduce(d_radiance)",
+                  l2="inputs larger than L2 (BVH+triangles 62 MB, SLF 64 MB+, hash grid 56 MB, per-tile records > 400 MB)")
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sc = scenes.cornell() if a.workload == "c1" else scenes.room(w["tris"], w["emitters"], seed=0)
+        config["triangles"] = sc.n_tris
+        cb, per = cpu_leg(w, sc, a.cpu_sample_pixels, a.steps, a.warmup)
+        line = dict(metric="path_samples_per_sec_fwd_bwd", value=cb["value"], unit="samples/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=per * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                    impl="reference", cpu_baseline=cb, e2e=dict(value=cb["value"], unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import torch
+    from iris_b200 import core
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    sc = scenes.cornell() if a.workload == "c1" else scenes.room(w["tris"], w["emitters"], seed=0)
+    config["triangles"] = sc.n_tris
+    scene = core.Scene(sc.vertices, sc.faces, local)
+    stats = scene.stats()
+    tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(256), bench_params(), sc.voxel_bounds())
+    views = [rank * w["views"] + v + 1 for v in range(w["views"])]
+    rays_host = torch.cat([torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=v)) for v in views]).pin_memory()
+    rays_dev = rays_host.to(dev)
+    P = rays_host.shape[0]
+    spp = w["spp"]
+    tile = min(a.tile, P)
+    lib = core.C.lib()
+    ws = torch.empty(lib.iris_single_workspace_bytes(tile, spp), dtype=torch.uint8, device=dev)
+    recs = [torch.empty(lib.iris_single_record_bytes(tile, spp), dtype=torch.uint8, device=dev) for _ in range(n_chunks)]
+    target = torch.full((P, 3), 0.5, device=dev)
+    n_samples_rank = P * w["SPP"]
+    step_no = [0]
+
+    def step(host_inputs):
+        """One training step of this rank: returns (loss tensor, d_radiance)."""
+        d_rad = torch.zeros(tables.K, 3, device=dev)
+        loss = torch.zeros((), device=dev)
+        s = step_no[0]
+        step_no[0] += 1
+        for t0 in range(0, P, tile):
+            t1 = min(t0 + tile, P)
+            rays = rays_host[t0:t1].to(dev, non_blocking=True) if host_inputs else rays_dev[t0:t1]
+            L = torch.zeros(t1 - t0, 3, device=dev)
+            for c in range(n_chunks):
+                smp = core.Sampler(seed=1000 + s, lane_offset=(t0 * n_chunks + c * (t1 - t0)) * spp)
+                Lc = torch.empty(t1 - t0, 3, device=dev)
+                P_, S_ = tables.c(), smp.c()
+                core.C.check(lib.iris_single_forward(scene.handle, P_, core.C.ptr(rays), t1 - t0, spp, S_, core.C.ptr(Lc), core.C.ptr(recs[c]),
+                                                     core.C.ptr(ws), ws.numel(), core.C.stream_ptr()))
+                L += Lc
+            L /= n_chunks
+            diff = L - target[t0:t1]
+            loss += (diff * diff).sum() / (P * 3 * world)
+            dL = diff * (2.0 / (P * 3 * world * n_chunks))
+            for c in range(n_chunks):
+                P_ = tables.c()
+                core.C.check(lib.iris_single_backward(P_, core.C.ptr(dL), t1 - t0, spp, core.C.ptr(recs[c]), core.C.ptr(d_rad), None, None, 0,
+                                                      core.C.stream_ptr()))
+        if dist is not None:
+            dist.all_reduce(d_rad)
+            dist.all_reduce(loss)
+        if host_inputs:
+            return loss.cpu(), d_rad.cpu()
+        return loss, d_rad
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host_inputs, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = step(host_inputs)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    # ---- warm-up, then the timed region (inputs resident in HBM)
+    for _ in range(max(a.warmup, 3)):
+        step(False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    lib.iris_profile_enable(1)
+    for k in range(8):
+        lib.iris_profile_read(k, None, None, 1)
+    l0 = lib.iris_launch_count()
+    ms, (loss, d_rad) = timed(False, a.steps)
+    launches = lib.iris_launch_count() - l0
+    prof = {}
+    for k in range(8):
+        n_, t_ = core.C.c_i64(), core.C.ctypes.c_double()
+        lib.iris_profile_read(k, core.C.ctypes.byref(n_), core.C.ctypes.byref(t_), 1)
+        if n_.value:
+            prof[lib.iris_profile_name(k).decode()] = dict(launches=n_.value, total_ms=t_.value)
+    lib.iris_profile_enable(0)
+    clk = clocks.stop() if rank == 0 else None
+    value = n_samples_rank * world * a.steps / (ms * 1e-3)
+
+    # ---- the same steps end to end: rays in pinned host memory, loss + gradient read back
+    e2e = None
+    if not a.no_e2e:
+        step(True)
+        ms_e, _ = timed(True, a.steps)
+        e2e = dict(value=n_samples_rank * world * a.steps / (ms_e * 1e-3), unit="samples/s", h2d_bytes_per_step=int(P * 12 * 4 * world),
+                   d2h_bytes_per_step=int((tables.K * 3 + 1) * 4 * world), ms_per_step=ms_e / a.steps)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_bounce_single: 2 of the 3 ray casts + BSDF/emitter/SLF/MIS + record)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    R = ray_bytes(sc.n_tris)
+    est_bytes = 3 * R + 1024 + 16 + 72.0 / spp            # SURVEY 8d, emitter-gradient `single` estimator
+    kb = prof.get("k_bounce_single")
+    roof = None
+    if kb:
+        k_bytes = 2 * R + 16 + 24.0 / spp                   # this kernel's share: 2 casts + SLF + pixel out/dL
+        per_launch_samples = n_samples_rank * a.steps / kb["launches"]
+        avg_ms = kb["total_ms"] / kb["launches"]
+        ach = per_launch_samples * k_bytes / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bounce_single")
+        except Exception:
+            pass
+        roof = dict(bound="hbm", kernel="k_bounce_single", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
+                    peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", algorithmic_bytes_per_sample=k_bytes,
+                    samples_per_launch=per_launch_samples, avg_launch_ms=avg_ms,
+                    step=dict(algorithmic_bytes_per_sample=est_bytes, achieved=value / max(world, 1) * est_bytes / 1e9, frac=value / max(world, 1) * est_bytes / 1e9 / peak),
+                    kernel_share_of_step={k: v["total_ms"] / ms for k, v in prof.items()})
+
+    cb = None
+    if not a.no_cpu_baseline and world == 1:
+        cb, _ = cpu_leg(w, sc, a.cpu_sample_pixels, 1, 1)
+
+    line = dict(metric="path_samples_per_sec_fwd_bwd", value=value, unit="samples/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cb,
+                scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
+                loss=float(loss), d_radiance_abs_sum=float(d_rad.abs().sum()))
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

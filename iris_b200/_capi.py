@@ -51,6 +51,9 @@ PROTOTYPES = {
                                            c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_single_backward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_launch_count": (c_i64, []),
+    "iris_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "iris_profile_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "iris_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
 }
 
 _LIB = None

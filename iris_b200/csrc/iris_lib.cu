@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/iris_b200.h"
 #include "bvh8.h"
@@ -36,6 +37,27 @@ static int fail(int code, const std::string &msg) {
         if (e__ != cudaSuccess) return fail(IRIS_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
     } while (0)
 
+// ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward"};
+struct ProfSpan { int id; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_spans;
+static std::vector<cudaEvent_t> g_free_events;
+static double g_prof_ms[K_COUNT] = {0};
+static int64_t g_prof_n[K_COUNT] = {0};
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_free_events.empty()) { e = g_free_events.back(); g_free_events.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    int id; cudaStream_t st; cudaEvent_t a{}, b{}; bool on;
+    ProfScope(int id_, cudaStream_t s) : id(id_), st(s), on(g_prof_on) { if (on) { a = prof_event(); b = prof_event(); cudaEventRecord(a, st); } }
+    ~ProfScope() { if (on) { cudaEventRecord(b, st); g_spans.push_back({id, a, b}); } }
+};
+
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + IRIS_BLOCK - 1) / IRIS_BLOCK); }
 static inline SceneView view_of(const IrisScene *s) {
     SceneView v;
@@ -66,6 +88,30 @@ extern "C" {
 const char *iris_last_error(void) { return g_err.c_str(); }
 const char *iris_version(void) { return "iris_b200 0.1 sm_100a"; }
 int64_t iris_launch_count(void) { return g_launches.load(); }
+
+int iris_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return IRIS_OK;
+}
+const char *iris_profile_name(int kernel_id) { return kernel_id >= 0 && kernel_id < K_COUNT ? g_kernel_names[kernel_id] : nullptr; }
+int iris_profile_read(int kernel_id, int64_t *launches, double *total_ms, int reset) {
+    if (kernel_id < 0 || kernel_id >= K_COUNT) return fail(IRIS_ERR_INVALID, "bad kernel id");
+    for (auto &sp : g_spans) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(sp.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
+        if (e != cudaSuccess) return fail(IRIS_ERR_CUDA, std::string("profile: ") + cudaGetErrorString(e));
+        g_prof_ms[sp.id] += ms;
+        g_prof_n[sp.id] += 1;
+        g_free_events.push_back(sp.a);
+        g_free_events.push_back(sp.b);
+    }
+    g_spans.clear();
+    if (launches) *launches = g_prof_n[kernel_id];
+    if (total_ms) *total_ms = g_prof_ms[kernel_id];
+    if (reset) { g_prof_n[kernel_id] = 0; g_prof_ms[kernel_id] = 0.0; }
+    return IRIS_OK;
+}
 
 int64_t iris_field_levels(float *scale, uint32_t *res, uint32_t *size, uint32_t *offset) {
     FieldLevel lv[FIELD_LEVELS];
@@ -142,7 +188,10 @@ int iris_intersect(const IrisScene *s, const float *o, const float *d, int64_t n
     if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
     if (n == 0) return IRIS_OK;
     if (!o || !d) return fail(IRIS_ERR_INVALID, "ray arrays are NULL");
-    k_intersect<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+    {
+        ProfScope ps(K_INTERSECT, (cudaStream_t)stream);
+        k_intersect<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+    }
     LAUNCHED();
     return IRIS_OK;
 }
@@ -190,6 +239,7 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
     CUDA_TRY(cudaMemsetAsync(out0, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     if (mode == 1) CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     const int64_t n = n_pixels * spp;
+    ProfScope ps(mode == 0 ? K_BAKE_DIFFUSE : K_BAKE_SPECULAR, st);
     if (mode == 0) k_bake<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
     else k_bake<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
     LAUNCHED();
@@ -205,6 +255,7 @@ static int launch_field(const IrisShadeParams *P, int64_t n, const float *positi
     }
     const int64_t tiles = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 4);
+    ProfScope ps(K_FIELD_FORWARD, st);
     if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
     else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
     LAUNCHED();
@@ -248,10 +299,14 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
     const int64_t n = n_pixels * spp;
     float4 *w0 = reinterpret_cast<float4 *>(workspace), *w1 = w0 + n, *w2 = w1 + n;
     CUDA_TRY(cudaMemsetAsync(L, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
-    k_primary<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1);
+    {
+        ProfScope ps(K_PRIMARY, st);
+        k_primary<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1);
+    }
     LAUNCHED();
     rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st);
     if (rc) return rc;
+    ProfScope ps(K_BOUNCE_SINGLE, st);
     if (record) k_bounce_single<true><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, reinterpret_cast<float4 *>(record));
     else k_bounce_single<false><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, nullptr);
     LAUNCHED();
@@ -272,6 +327,7 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
     const size_t smem = K <= IRIS_BWD_KMAX ? (size_t)3 * K * IRIS_BLOCK * 4 : 0;
     const int64_t n = n_pixels * spp;
     const unsigned grid = (unsigned)std::min<int64_t>(blocks_for(n), (int64_t)g_sm_count * 8);
+    ProfScope ps(K_SINGLE_BACKWARD, st);
     k_single_backward<<<grid, IRIS_BLOCK, smem, st>>>(dL, n_pixels, spp, reinterpret_cast<const float4 *>(record), K, d_radiance, nullptr);
     LAUNCHED();
     return IRIS_OK;

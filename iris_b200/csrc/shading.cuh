@@ -63,8 +63,10 @@ __device__ __forceinline__ f3 diffuse_sampler(float u0, float u1, f3 n) {
 }
 // model/brdf.py:36-59
 __device__ __forceinline__ f3 specular_sampler(float u0, float u1, float roughness, f3 wo, f3 n) {
-    const float alpha = roughness * roughness;
-    const float c2 = (1.f - u0) / (u0 * (alpha * alpha - 1.f) + 1.f);
+    // (1-u0)/(u0*(alpha^2-1)+1) cancels catastrophically for small roughness: one rounding per op, in the reference's
+    // order, or the sampled lobe direction moves by whole quanta of acos near 1
+    const float alpha = xmul(roughness, roughness);
+    const float c2 = __fdiv_rn(xsub(1.f, u0), xadd(xmul(u0, xsub(xmul(alpha, alpha), 1.f)), 1.f));
     const f3 wh = sphere_to_world(acosf(sqrtf(c2)), (2.f * IRIS_PI) * u1, n);
     return normalize_nf((2.f * dot(wo, wh)) * wh - wo);
 }
@@ -80,12 +82,15 @@ struct Angles {
     float NoL, NoV, VoH, NoH;
 };
 __device__ __forceinline__ Angles angles(f3 wi, f3 wo, f3 n) {
-    const f3 h = normalize_nf(wi + wo);
+    // one rounding per op (the ATen chain of model/brdf.py:151-155): NoH feeds the ill-conditioned GGX denominator
+    const f3 s = mk3(xadd(wi.x, wo.x), xadd(wi.y, wo.y), xadd(wi.z, wo.z));
+    const float l = fmaxf(__fsqrt_rn(xdot(s, s)), 1e-12f);
+    const f3 h = mk3(__fdiv_rn(s.x, l), __fdiv_rn(s.y, l), __fdiv_rn(s.z, l));
     Angles a;
-    a.NoL = fmaxf(dot(wi, n), 0.f);
-    a.NoV = fmaxf(dot(wo, n), 0.f);
-    a.VoH = fmaxf(dot(wo, h), 0.f);
-    a.NoH = fmaxf(dot(n, h), 0.f);
+    a.NoL = fmaxf(xdot(wi, n), 0.f);
+    a.NoV = fmaxf(xdot(wo, n), 0.f);
+    a.VoH = fmaxf(xdot(wo, h), 0.f);
+    a.NoH = fmaxf(xdot(n, h), 0.f);
     return a;
 }
 __device__ __forceinline__ float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
@@ -100,9 +105,11 @@ template <bool JAC>
 __device__ __forceinline__ void eval_brdf(f3 wi, f3 wo, f3 n, const Mat &mat, f3 &f, float &pdf, BrdfJac *J) {
     const Angles g = angles(wi, wo, n);
     const float r = mat.r;
-    const float a2 = (r * r) * (r * r);
-    const float den = g.NoH * g.NoH * (a2 - 1.f) + 1.f;
-    const float D = a2 / (IRIS_PI * den * den);
+    // utils/ops.py:74-82 in its own op order, one rounding each: den = NoH^2 (a2-1) + 1 cancels for small roughness
+    const float al = xmul(r, r);
+    const float a2 = xmul(al, al);
+    const float den = xadd(xmul(xmul(g.NoH, g.NoH), xsub(a2, 1.f)), 1.f);
+    const float D = __fdiv_rn(a2, xmul(xmul(IRIS_PI, den), den));
     pdf = 0.5f * (D / (4.f * fmaxf(g.VoH, 1e-4f)) * g.NoH) + 0.5f * (g.NoL / IRIS_PI);
     const float om = 1.f - mat.m;
     const f3 kd = mat.a * om;
