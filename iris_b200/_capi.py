@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libiris_b200.so")
+LIB_PATH = os.environ.get("IRIS_B200_LIB") or os.path.join(HERE, "_lib", "libiris_b200.so")   # override: A/B builds of the same ABI
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 

@@ -20,7 +20,8 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force=False, verbose=False, extra=()):
+def build(force=False, verbose=False, extra=(), out=None):
+    OUT = out or globals()["OUT"]
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "iris_b200.h")]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest(deps):
@@ -34,4 +35,7 @@ def build(force=False, verbose=False, extra=()):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "-v" in sys.argv else [])
+    # python iris_b200/build.py [--force] [-v] [--out path.so] [-DNAME=VALUE ...]
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    build(force="--force" in sys.argv or out is not None, verbose=True, extra=(["-Xptxas", "-v"] if "-v" in sys.argv else []) + defs, out=out)

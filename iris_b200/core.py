@@ -41,8 +41,8 @@ class Scene:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            C.lib().iris_scene_destroy(h)
+        if h and C is not None and getattr(C, "_LIB", None) is not None:      # (module globals may be gone at interpreter exit)
+            C._LIB.iris_scene_destroy(h)
             self._h = None
 
     @property

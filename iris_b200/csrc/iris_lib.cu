@@ -139,7 +139,7 @@ int iris_scene_create(const float *verts, int64_t n_verts, const int32_t *faces,
     const auto t0 = std::chrono::steady_clock::now();
     HostBvh hb;
     if (host_bvh_build(verts, n_verts, faces, n_faces, &hb) != 0) return fail(IRIS_ERR_NOMEM, "host BVH build failed");
-    if (hb.max_depth > IRIS_STACK) {
+    if (2 * hb.max_depth > IRIS_STACK) {
         host_bvh_free(&hb);
         return fail(IRIS_ERR_INVALID, "BVH deeper than the traversal stack (" + std::to_string(hb.max_depth) + " levels)");
     }

@@ -137,8 +137,11 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_primary(SceneView S, IrisShadePa
 //   r1 = (c_nee.xyz, c_b.x)         dL/dradiance[e_nee] = g * c_nee,  dL/dradiance[e_b] = g * c_b,  dL/dradiance[e0] = g
 //   r2 = (c_b.yz, Ja.xy)   r3 = (Ja.z, Jr.xyz)   r4 = (Jm.xyz, -)     J* = d(L_c)/d(albedo_c | roughness | metallic)
 //   r5 = (x0.xyz, code)
+#ifndef IRIS_BOUNCE_MINBLOCKS
+#define IRIS_BOUNCE_MINBLOCKS 5
+#endif
 template <bool RECORD>
-__global__ void __launch_bounds__(IRIS_BLOCK) k_bounce_single(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
+__global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_single(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
                                                                int64_t n_pixels, int spp, const float4 *__restrict__ w0,
                                                                const float4 *__restrict__ w1, const float4 *__restrict__ w2, float *L_out,
                                                                float4 *__restrict__ rec) {
@@ -166,37 +169,38 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_bounce_single(SceneView S, IrisS
             const float4 ua = sample4(smp, i, 0), ub = sample4(smp, i, 1);
             const f3 wo = -camera_dir(rays, pix, ua.x, ua.y);
             // ---- emitter sampling + shadow ray + MIS (utils/path_tracing.py:359-382)
+            // The reference casts a closest-hit ray and keeps the sample only if the hit triangle IS the sampled emitter
+            // triangle (a miss contributes Le = 0).  Equivalent and cheaper: intersect the sampled triangle directly, then
+            // ask whether anything beats it under the closest-hit ordering (any-hit query bounded by its t).
             {
                 f3 wi;
                 float pdf_e;
                 int32_t e, face;
                 sample_emitter(P, ua.z, ua.w, ub.x, x0, wi, pdf_e, e, face);
                 const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
-                const Hit h = trace_closest(S, org, wi);
-                f3 hp, hn;
-                hit_surface(S, h, wi, hp, hn);
-                const bool hit = h.prim >= 0;
-                const bool vis = !hit || h.prim == face;
-                const int32_t eh = emitter_of(P, h.prim);
-                float G = 1.f;
-                if (hit) {
+                f3 v0, e1, e2;
+                emitter_triangle(P, e, v0, e1, e2);
+                float tl, bu, bv;
+                if (tri_test(org, wi, __fdiv_rn(1.0f, xdot(wi, wi)), v0, e1, e2, tl, bu, bv) && !trace_occluded(S, org, wi, tl, face)) {
+                    Hit h;
+                    h.t = tl; h.u = bu; h.v = bv; h.prim = face; h.slot = -1;
+                    f3 hp, hn;
+                    surface_from_triangle(h, wi, v0, e1, e2, hp, hn);
                     const f3 dlt = hp - x0;
-                    G = fabsf(-(wi.x * hn.x) - (wi.y * hn.y) - (wi.z * hn.z)) / fmaxf(dot(dlt, dlt), 1e-6f);
-                }
-                f3 f;
-                float pdf_b;
-                BrdfJac J;
-                eval_brdf<RECORD>(wi, wo, n0, mat, f, pdf_b, &J);
-                pdf_b *= G;
-                float w = (pdf_e > 0.f && !isinf(pdf_b)) ? pdf_e * pdf_e / fmaxf(pdf_e * pdf_e + pdf_b * pdf_b, 1e-6f) : 0.f;
-                if (isinf(pdf_e) || pdf_b == 0.f) w = 1.f;
-                const float s = (vis ? 1.f : 0.f) * G / fmaxf(pdf_e, 1e-6f) * w;
-                if (hit && eh >= 0) {
-                    const f3 Le = emitter_radiance(P, eh);
-                    const f3 W = Le * s;
+                    const float G = fabsf(-(wi.x * hn.x) - (wi.y * hn.y) - (wi.z * hn.z)) / fmaxf(dot(dlt, dlt), 1e-6f);
+                    f3 f;
+                    float pdf_b;
+                    BrdfJac J;
+                    eval_brdf<RECORD>(wi, wo, n0, mat, f, pdf_b, &J);
+                    pdf_b *= G;
+                    float w = (pdf_e > 0.f && !isinf(pdf_b)) ? pdf_e * pdf_e / fmaxf(pdf_e * pdf_e + pdf_b * pdf_b, 1e-6f) : 0.f;
+                    if (isinf(pdf_e) || pdf_b == 0.f) w = 1.f;
+                    const float s = G / fmaxf(pdf_e, 1e-6f) * w;
+                    const f3 W = emitter_radiance(P, e) * s;
                     L = L + f * W;
                     if (RECORD) {
-                        if (vis) { e_nee = eh; c_nee = f * s; }
+                        e_nee = e;
+                        c_nee = f * s;
                         Ja = Ja + J.da * W; Jr = Jr + J.dr * W; Jm = Jm + J.dm * W;
                     }
                 }

@@ -195,6 +195,16 @@ __device__ __forceinline__ float emitter_pdf_area(const IrisShadeParams &P, int3
     return __ldg(P.emitter_pdf + e) / fmaxf(__ldg(P.emitter_area + e), 1e-12f);
 }
 
+// The sampled emitter triangle as the BVH stores it (v0, e1 = v1 - v0, e2 = v2 - v0 rounded once; zero-area -> never hit)
+__device__ __forceinline__ void emitter_triangle(const IrisShadeParams &P, int32_t e, f3 &v0, f3 &e1, f3 &e2) {
+    const float *V = P.emitter_vertices + 9 * (int64_t)e;
+    v0 = mk3(__ldg(V + 0), __ldg(V + 1), __ldg(V + 2));
+    e1 = mk3(xsub(__ldg(V + 3), v0.x), xsub(__ldg(V + 4), v0.y), xsub(__ldg(V + 5), v0.z));
+    e2 = mk3(xsub(__ldg(V + 6), v0.x), xsub(__ldg(V + 7), v0.y), xsub(__ldg(V + 8), v0.z));
+    const f3 c = xcross(e1, e2);
+    if (c.x == 0.f && c.y == 0.f && c.z == 0.f) { e1 = mk3(0.f, 0.f, 0.f); e2 = e1; }
+}
+
 // model/emitter.py:224-255
 __device__ __forceinline__ void sample_emitter(const IrisShadeParams &P, float u1, float u2x, float u2y, f3 x, f3 &wi, float &pdf,
                                                int32_t &e, int32_t &face) {

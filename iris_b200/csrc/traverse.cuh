@@ -9,7 +9,7 @@
 #include "bvh8.h"
 #include "common.cuh"
 
-#define IRIS_STACK 32
+#define IRIS_STACK 48   // one node group + one postponed triangle group per level: 2 * depth <= IRIS_STACK
 
 struct SceneView {
     const float4 *nodes;   // 5 per node
@@ -32,7 +32,17 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     return r;
 #endif
 }
-__device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+// byte j of w as a float, exactly, without the conversion unit: 0x4B0000bb is the float 2^23 + bb, so one PRMT (ALU pipe)
+// and one FADD (FMA pipe) replace an I2F.U8 that would otherwise saturate the XU pipe (48 conversions per node visit)
+__device__ __forceinline__ float byte_f(uint32_t w, int j) {
+#ifdef IRIS_HOST_EMULATION
+    return (float)((w >> (8 * j)) & 0xFFu);
+#else
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(0x7440u + (uint32_t)j));
+    return __uint_as_float(r) - 8388608.0f;
+#endif
+}
 
 // Moller-Trumbore barycentrics + projected t, operation order of oracle/intersect.c:tri_test (rdd = 1/(d.d))
 __device__ __forceinline__ bool tri_test(f3 o, f3 d, float rdd, f3 v0, f3 e1, f3 e2, float &t, float &u, float &v) {
@@ -63,11 +73,15 @@ __device__ __forceinline__ void load_tri(const SceneView &S, int32_t slot, f3 &v
     prim = __float_as_int(c.y);
 }
 
-__device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
+// ANYHIT = false: closest hit (minimum t, ties to the lowest prim index).
+// ANYHIT = true : occlusion query against a known candidate (t_limit, prim_limit): returns as soon as some triangle beats the
+//                 candidate under the same ordering (t < t_limit, or t == t_limit and prim < prim_limit); best.slot >= 0 then.
+template <bool ANYHIT>
+__device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit) {
     Hit best;
-    best.t = __int_as_float(0x7f800000);
+    best.t = t_limit;
     best.u = best.v = 0.f;
-    best.prim = -1;
+    best.prim = prim_limit;
     best.slot = -1;
 
     uint2 stack[IRIS_STACK];
@@ -138,7 +152,18 @@ __device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
             tgroup = ngroup;
             ngroup = make_uint2(0u, 0u);
         }
+#if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
+        // triangle postponing (Ylitie et al. 2017): when fewer than ~20% of the lanes that entered the triangle phase are
+        // still testing triangles, the stragglers park their remaining triangles on the stack and go back to node work
+        const int tri_lanes = __popc(__activemask());
+#endif
         while (tgroup.y != 0u) {
+#if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
+            if (__popc(__activemask()) * 5 < tri_lanes && sp < IRIS_STACK - 1) {
+                stack[sp++] = tgroup;
+                break;
+            }
+#endif
             const uint32_t ti = 31u - __clz(tgroup.y);
             tgroup.y &= ~(1u << ti);
             const int32_t slot = (int32_t)(tgroup.x + ti);
@@ -149,6 +174,7 @@ __device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
             if (tri_test(o, d, rdd, v0, e1, e2, t, u, v)) {
                 if (t < best.t || (t == best.t && prim < best.prim)) {
                     best.t = t; best.u = u; best.v = v; best.prim = prim; best.slot = slot;
+                    if (ANYHIT) return best;
                 }
             }
         }
@@ -160,16 +186,26 @@ __device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
     return best;
 }
 
+__device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
+    return trace_ray<false>(S, o, d, __int_as_float(0x7f800000), -1);
+}
+__device__ __forceinline__ bool trace_occluded(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit) {
+    return trace_ray<true>(S, o, d, t_limit, prim_limit).slot >= 0;
+}
+
 // Surface record of a hit: p = fma(v,e2,fma(u,e1,v0)), n = normalize(e1 x e2) flipped toward -d (oracle finish()).
-__device__ __forceinline__ void hit_surface(const SceneView &S, const Hit &h, f3 d, f3 &p, f3 &n) {
-    if (h.prim < 0) { p = mk3(0.f, 0.f, 0.f); n = mk3(0.f, 0.f, 0.f); return; }
-    f3 v0, e1, e2;
-    int32_t prim;
-    load_tri(S, h.slot, v0, e1, e2, prim);
+__device__ __forceinline__ void surface_from_triangle(const Hit &h, f3 d, f3 v0, f3 e1, f3 e2, f3 &p, f3 &n) {
     p = mk3(__fmaf_rn(h.v, e2.x, __fmaf_rn(h.u, e1.x, v0.x)), __fmaf_rn(h.v, e2.y, __fmaf_rn(h.u, e1.y, v0.y)),
             __fmaf_rn(h.v, e2.z, __fmaf_rn(h.u, e1.z, v0.z)));
     f3 c = xcross(e1, e2);
     float len = __fsqrt_rn(xdot(c, c));
     n = mk3(__fdiv_rn(c.x, len), __fdiv_rn(c.y, len), __fdiv_rn(c.z, len));
     if (xdot(n, d) > 0.0f) n = -n;
+}
+__device__ __forceinline__ void hit_surface(const SceneView &S, const Hit &h, f3 d, f3 &p, f3 &n) {
+    if (h.prim < 0) { p = mk3(0.f, 0.f, 0.f); n = mk3(0.f, 0.f, 0.f); return; }
+    f3 v0, e1, e2;
+    int32_t prim;
+    load_tri(S, h.slot, v0, e1, e2, prim);
+    surface_from_triangle(h, d, v0, e1, e2, p, n);
 }
