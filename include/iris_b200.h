@@ -133,8 +133,9 @@ int iris_bake(const IrisScene *scene, const IrisShadeParams *params, int mode, f
 /* Hash-grid level table (32 entries each): returns the total number of grid entries (13 977 056). */
 int64_t iris_field_levels(float *scale, uint32_t *res, uint32_t *size, uint32_t *offset);
 int iris_field_forward(const IrisShadeParams *params, const float *position, int64_t n, float *mat, void *stream);
+int64_t iris_field_backward_workspace_bytes(int64_t n);
 int iris_field_backward(const IrisShadeParams *params, const float *position, const float *d_mat, int64_t n,
-                        float *d_params, void *stream);
+                        float *d_params, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * path_tracing_single forward + adjoint (utils/path_tracing.py:320-407), the estimator
@@ -163,7 +164,7 @@ int64_t iris_launch_count(void);
 
 /* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its own stream.
  * iris_profile_read synchronises the pending events and returns the launch count and the summed duration of one
- * kernel class (ids 0..7, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */
+ * kernel class (ids 0..8, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */
 int iris_profile_enable(int on);
 const char *iris_profile_name(int kernel_id);
 int iris_profile_read(int kernel_id, int64_t *launches, double *total_ms, int reset);

@@ -204,6 +204,24 @@ def field_forward(tables, position):
     return mat
 
 
+def field_backward(tables, position, d_mat, d_params=None, workspace=None):
+    """Adjoint of NGPBRDF.forward: accumulates into d_params (flat fp32 [mlp 9216 | grid], tcnn layout) and returns it."""
+    position = position.contiguous().float()
+    d_mat = d_mat.contiguous().float()
+    n = position.shape[0]
+    dev = position.device
+    if d_params is None:
+        d_params = torch.zeros(N_MLP + tables.t["grid_f16"].numel(), device=dev)
+    lib = C.lib()
+    wb = lib.iris_field_backward_workspace_bytes(n)
+    if workspace is None or workspace.numel() < wb:
+        workspace = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
+    P = tables.c()
+    with torch.cuda.device(dev):
+        C.check(lib.iris_field_backward(ctypes.byref(P), C.ptr(position), C.ptr(d_mat), n, C.ptr(d_params), C.ptr(workspace), workspace.numel(), C.stream_ptr()))
+    return d_params
+
+
 def single_forward(scene, tables, rays, spp, sampler, want_record=False, workspace=None):
     """path_tracing_single forward.  Returns (L (B,3), record or None)."""
     rays = rays.contiguous().float()

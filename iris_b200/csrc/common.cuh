@@ -19,8 +19,12 @@ __device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y
 __device__ __forceinline__ f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-// NF.normalize: v / max(|v|, 1e-12)
-__device__ __forceinline__ f3 normalize_nf(f3 a) { float l = fmaxf(sqrtf(dot(a, a)), 1e-12f); return mk3(a.x / l, a.y / l, a.z / l); }
+// NF.normalize: v / max(|v|, 1e-12).  |v|^2 is accumulated as fma(z,z,fma(y,y,x*x)) -- the order torch's CPU vector_norm uses for a
+// 3-vector (checked bit for bit) -- and every step is a single IEEE rounding, so directions match the reference's CPU run.
+__device__ __forceinline__ f3 normalize_nf(f3 a) {
+    const float l = fmaxf(__fsqrt_rn(__fmaf_rn(a.z, a.z, __fmaf_rn(a.y, a.y, __fmul_rn(a.x, a.x)))), 1e-12f);
+    return mk3(__fdiv_rn(a.x, l), __fdiv_rn(a.y, l), __fdiv_rn(a.z, l));
+}
 __device__ __forceinline__ f3 ld3(const float *p, int64_t i) { return mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
 __device__ __forceinline__ void st3(float *p, int64_t i, f3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
 

@@ -229,3 +229,392 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P,
         }
     }
 }
+
+// =====================================================================================================================
+// Adjoint of the field: d_mat (n,5) -> d_params ([W1|W2|W3 | grid], fp32, tcnn's flat layout).
+//
+// Kernel A (k_field_backward_dgrad), one warp per 32 samples: re-encode, forward with ReLU masks kept as register bit masks,
+// dy = d_mat * d(sigmoid) normalised per sample to [-1,1] by a power of two s_i (fp16 range), dgrad through W3, W2, W1 on
+// tensor cores (transposed weights resident in shared memory), scatter of s_i * w_corner * dx into the grid gradient with
+// vectorised reductions (red.global.add.v2.f32).  Activations X,h1,h2 and the normalised dh2^,dh1^,dy^ are streamed to HBM
+// with coalesced 16-byte stores.
+// Kernel B (k_field_backward_wgrad): dW = sum_i s_i * dh^_i (x) h_i as a split-K TF32 GEMM over the samples, accumulators in
+// registers for the whole chunk, then ONE atomic per weight per CTA.
+// Gradient semantics = oracle/field.py: straight-through across every fp16 rounding, sigmoid' from the fp32 sigmoid.
+// =====================================================================================================================
+#define FIELD_LD3 24   // leading dimension (halfs) of the 16-wide operands (dy^, W3^T)
+#define FIELD_BWD_WSM_HALFS ((64 + 64 + 16) * FIELD_LD + 2 * 64 * FIELD_LD + 64 * FIELD_LD3)
+#define FIELD_BWD_SMEM_BYTES (FIELD_BWD_WSM_HALFS * 2 + (IRIS_BLOCK / 32) * 32 * FIELD_LD * 2)
+#define FIELD_ACT_BYTES_PER_SAMPLE (5 * 128 + 32 + 4)   // X h1 h2 dh2^ dh1^ (64 halfs each) | dy^ (16 halfs) | s (float)
+
+struct FieldAct {   // SoA activation streams of one chunk of n samples
+    __half *X, *h1, *h2, *dh2, *dh1, *dy;
+    float *s;
+};
+__host__ __device__ inline FieldAct field_act_carve(void *base, int64_t n) {
+    FieldAct a;
+    __half *p = reinterpret_cast<__half *>(base);
+    a.X = p; a.h1 = p + 64 * n; a.h2 = p + 128 * n; a.dh2 = p + 192 * n; a.dh1 = p + 256 * n; a.dy = p + 320 * n;
+    a.s = reinterpret_cast<float *>(p + 336 * n);
+    return a;
+}
+
+// coalesced copy of a warp's 32 x 64 fp16 tile (shared, ld FIELD_LD) to rows [row0, row0+32) of a [n][64] global array
+__device__ __forceinline__ void warp_tile_to_global(const __half *Xs, __half *dst, int64_t row0, int64_t n) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int v = it * 32 + lane;          // 256 vectors of 8 halfs
+        const int r = v >> 3, c = (v & 7) * 8;
+        if (row0 + r < n) *reinterpret_cast<uint4 *>(dst + (row0 + r) * 64 + c) = *reinterpret_cast<const uint4 *>(Xs + r * FIELD_LD + c);
+    }
+}
+
+__device__ __forceinline__ uint32_t relu_mask_bits(const float acc[8][4]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m |= (acc[nt][k] > 0.f ? 1u : 0u) << (nt * 4 + k);
+    return m;
+}
+
+// out[mt][nt][4] = A(32 x KT*16, fp16, ld lda) * B with B given TRANSPOSED in shared memory: BT[n][k] (ld ldb)
+template <int NT, int KT>
+__device__ __forceinline__ void warp_gemm_t(const __half *A, int lda, const __half *BT, int ldb, float acc[2][NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+        const int k0 = 16 * kk + 2 * t;
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const __half *r0 = A + (16 * mt + g) * lda + k0, *r1 = r0 + 8 * lda;
+            a[mt][0] = *reinterpret_cast<const uint32_t *>(r0);
+            a[mt][1] = *reinterpret_cast<const uint32_t *>(r1);
+            a[mt][2] = *reinterpret_cast<const uint32_t *>(r0 + 8);
+            a[mt][3] = *reinterpret_cast<const uint32_t *>(r1 + 8);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const __half *w = BT + (8 * nt + g) * ldb + k0;
+            uint32_t b[2];
+            b[0] = *reinterpret_cast<const uint32_t *>(w);
+            b[1] = *reinterpret_cast<const uint32_t *>(w + 8);
+            mma16816(acc[0][nt], a[0], b);
+            mma16816(acc[1][nt], a[1], b);
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// WS = true: positions/flags from the estimator record word r5 (x0.xyz, code), d_mat from the workspace; WS = false: plain arrays
+template <bool WS>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_dgrad(IrisShadeParams P, int64_t n, const float *__restrict__ position,
+                                                                      const float4 *__restrict__ r5, const float *__restrict__ d_mat,
+                                                                      FieldAct act, float *__restrict__ d_grid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half *Wsm = reinterpret_cast<__half *>(smem_raw);              // W1 | W2 | W3 (forward, [out][in])
+    __half *W1T = Wsm + (64 + 64 + 16) * FIELD_LD;                     // [in][out] copies for dgrad
+    __half *W2T = W1T + 64 * FIELD_LD;
+    __half *W3T = W2T + 64 * FIELD_LD;                                 // [in=64][out=16], ld FIELD_LD3
+    __half *Xs = Wsm + FIELD_BWD_WSM_HALFS + (threadIdx.x >> 5) * 32 * FIELD_LD;
+    const __half *mlp = reinterpret_cast<const __half *>(P.mlp_f16);
+    field_load_weights(mlp, Wsm);
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const int o = i >> 6, in = i & 63;
+        W1T[in * FIELD_LD + o] = mlp[i];
+        W2T[in * FIELD_LD + o] = mlp[4096 + i];
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+        const int o = i >> 6, in = i & 63;
+        W3T[in * FIELD_LD3 + o] = mlp[8192 + i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const __half2 *grid = reinterpret_cast<const __half2 *>(P.grid_f16);
+    const int64_t n_tiles = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * IRIS_BLOCK + (threadIdx.x & ~31);
+        const int64_t i = row0 + lane;
+        bool active = i < n;
+        f3 p = mk3(0.f, 0.f, 0.f);
+        float dm[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (active) {
+            if (WS) {
+                const float4 a = r5[i];
+                active = __float_as_int(a.w) == -2;
+                p = mk3(a.x, a.y, a.z);
+            } else {
+                p = ld3(position, i);
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) dm[k] = d_mat[5 * i + k];
+            active = active && (dm[0] != 0.f || dm[1] != 0.f || dm[2] != 0.f || dm[3] != 0.f || dm[4] != 0.f);
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            // nothing to do for these 32 samples: the wgrad kernel must still see zeros
+            if (i < n) {
+                act.s[i] = 0.f;
+                *reinterpret_cast<uint4 *>(act.dy + 16 * i) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(act.dy + 16 * i + 8) = make_uint4(0, 0, 0, 0);
+            }
+            uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int v = it * 32 + lane, r = v >> 3, c = (v & 7) * 8;
+                if (row0 + r < n) {
+                    *reinterpret_cast<uint4 *>(act.X + (row0 + r) * 64 + c) = z;
+                    *reinterpret_cast<uint4 *>(act.h1 + (row0 + r) * 64 + c) = z;
+                    *reinterpret_cast<uint4 *>(act.h2 + (row0 + r) * 64 + c) = z;
+                    *reinterpret_cast<uint4 *>(act.dh2 + (row0 + r) * 64 + c) = z;
+                    *reinterpret_cast<uint4 *>(act.dh1 + (row0 + r) * 64 + c) = z;
+                }
+            }
+            continue;
+        }
+        const f3 x = mk3(field_coord(p.x, P.field_vmin, P.field_range), field_coord(p.y, P.field_vmin, P.field_range),
+                         field_coord(p.z, P.field_vmin, P.field_range));
+        __half *row = Xs + lane * FIELD_LD;
+        if (active) {
+            field_encode(grid, x, row);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) *reinterpret_cast<__half2 *>(row + 2 * k) = __floats2half2_rn(0.f, 0.f);
+        }
+        __syncwarp();
+        warp_tile_to_global(Xs, act.X, row0, n);
+        // ---- forward, keeping the ReLU masks
+        float acc[2][8][4];
+        uint32_t m1[2], m2[2];
+        warp_gemm<8>(Xs, Wsm, acc);
+        m1[0] = relu_mask_bits(acc[0]); m1[1] = relu_mask_bits(acc[1]);
+        __syncwarp();
+        warp_store_relu(Xs, acc);
+        __syncwarp();
+        warp_tile_to_global(Xs, act.h1, row0, n);
+        warp_gemm<8>(Xs, Wsm + 64 * FIELD_LD, acc);
+        m2[0] = relu_mask_bits(acc[0]); m2[1] = relu_mask_bits(acc[1]);
+        __syncwarp();
+        warp_store_relu(Xs, acc);
+        __syncwarp();
+        warp_tile_to_global(Xs, act.h2, row0, n);
+        float out[2][2][4];
+        warp_gemm<2>(Xs, Wsm + 128 * FIELD_LD, out);
+        __syncwarp();
+        float *Ys = reinterpret_cast<float *>(Xs);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                float *r0 = Ys + (16 * mt + g) * 17 + 8 * nt + 2 * t;
+                r0[0] = out[mt][nt][0]; r0[1] = out[mt][nt][1];
+                r0[8 * 17] = out[mt][nt][2]; r0[8 * 17 + 1] = out[mt][nt][3];
+            }
+        __syncwarp();
+        // ---- dy = d_mat * d(mat)/dy, normalised per sample by a power of two
+        float dy[5];
+        float sc = 0.f;
+        {
+            const float *y = Ys + lane * 17;
+            float mx = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float yk = __half2float(__float2half_rn(y[k]));
+                const float s = 1.0f / (1.0f + expf(-yk));
+                dy[k] = active ? dm[k] * (k == 3 ? 0.98f : 1.0f) * s * (1.0f - s) : 0.f;
+                mx = fmaxf(mx, fabsf(dy[k]));
+            }
+            if (mx > 0.f && mx < __int_as_float(0x7f800000)) {
+                int e;
+                frexpf(mx, &e);               // mx = f * 2^e, f in [0.5,1)
+                sc = ldexpf(1.0f, e);         // mx / sc in [0.5,1)
+            }
+        }
+        __syncwarp();
+        __half *Dy = Xs + 32 * 36;            // after the Ys region (32*17 floats = 1088 halfs) -> halfs [1152, 1152+768)
+        {
+            const float inv = sc > 0.f ? 1.0f / sc : 0.f;
+            __half *d = Dy + lane * FIELD_LD3;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[k] = __float2half_rn(k < 5 ? dy[k] * inv : 0.f);
+            if (i < n) {
+                act.s[i] = sc;
+                *reinterpret_cast<uint4 *>(act.dy + 16 * i) = *reinterpret_cast<const uint4 *>(d);
+                *reinterpret_cast<uint4 *>(act.dy + 16 * i + 8) = *reinterpret_cast<const uint4 *>(d + 8);
+            }
+        }
+        __syncwarp();
+        // ---- dgrad: dh2^ = dy^ W3 (.) mask2 ; dh1^ = dh2^ W2 (.) mask1 ; dx^ = dh1^ W1
+        warp_gemm_t<8, 1>(Dy, FIELD_LD3, W3T, FIELD_LD3, acc);
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (!((m2[mt] >> (nt * 4 + k)) & 1u)) acc[mt][nt][k] = 0.f;
+        {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    __half *r0 = Xs + (16 * mt + g) * FIELD_LD + 8 * nt + 2 * t;
+                    *reinterpret_cast<__half2 *>(r0) = __floats2half2_rn(acc[mt][nt][0], acc[mt][nt][1]);
+                    *reinterpret_cast<__half2 *>(r0 + 8 * FIELD_LD) = __floats2half2_rn(acc[mt][nt][2], acc[mt][nt][3]);
+                }
+        }
+        __syncwarp();
+        warp_tile_to_global(Xs, act.dh2, row0, n);
+        warp_gemm_t<8, 4>(Xs, FIELD_LD, W2T, FIELD_LD, acc);
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (!((m1[mt] >> (nt * 4 + k)) & 1u)) acc[mt][nt][k] = 0.f;
+                __half *r0 = Xs + (16 * mt + g) * FIELD_LD + 8 * nt + 2 * t;
+                *reinterpret_cast<__half2 *>(r0) = __floats2half2_rn(acc[mt][nt][0], acc[mt][nt][1]);
+                *reinterpret_cast<__half2 *>(r0 + 8 * FIELD_LD) = __floats2half2_rn(acc[mt][nt][2], acc[mt][nt][3]);
+            }
+        __syncwarp();
+        warp_tile_to_global(Xs, act.dh1, row0, n);
+        warp_gemm_t<8, 4>(Xs, FIELD_LD, W1T, FIELD_LD, acc);
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                __half *r0 = Xs + (16 * mt + g) * FIELD_LD + 8 * nt + 2 * t;
+                *reinterpret_cast<__half2 *>(r0) = __floats2half2_rn(acc[mt][nt][0], acc[mt][nt][1]);
+                *reinterpret_cast<__half2 *>(r0 + 8 * FIELD_LD) = __floats2half2_rn(acc[mt][nt][2], acc[mt][nt][3]);
+            }
+        __syncwarp();
+        // ---- scatter s_i * w_corner * dx^ into the grid gradient (same indices / weights as the encoder)
+        if (active && sc > 0.f) {
+#pragma unroll 2
+            for (int l = 0; l < FIELD_LEVELS; ++l) {
+                const float2 dx = __half22float2(*reinterpret_cast<const __half2 *>(row + 2 * l));
+                const float gx = dx.x * sc, gy = dx.y * sc;
+                if (gx == 0.f && gy == 0.f) continue;
+                const FieldLevel L = c_levels[l];
+                const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
+                const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+                const float wx1 = xsub(px, fx), wy1 = xsub(py, fy), wz1 = xsub(pz, fz);
+                const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
+                const uint32_t cx = (uint32_t)__float2int_rz(fx), cy = (uint32_t)__float2int_rz(fy), cz = (uint32_t)__float2int_rz(fz);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
+                    uint32_t idx;
+                    if (L.dense) idx = (ix + iy * L.res + iz * L.res * L.res) % L.size;
+                    else idx = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1u);
+                    const float w = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
+                    red_add_v2(d_grid + 2 * (int64_t)(L.offset + idx), w * gx, w * gy);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void mma1688_tf32(float c[4], const uint32_t a[4], const uint32_t b[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// dW[o][i] += sum_s s_s * D[s][o] * H[s][i] for one 32-sample tile: warp w owns rows [16w,16w+16) (MT16 = number of 16-row
+// slices that exist: 4 for the 64-row matrices, 1 for W3)
+__device__ __forceinline__ void wgrad_tile(const __half *D, int ldd, const __half *H, const float *sc, int mrow0, float acc[8][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int k0 = 8 * ks;
+        const float s0 = sc[k0 + t], s1 = sc[k0 + t + 4];
+        uint32_t a[4];
+        a[0] = to_tf32(__half2float(D[(k0 + t) * ldd + mrow0 + g]) * s0);
+        a[1] = to_tf32(__half2float(D[(k0 + t) * ldd + mrow0 + g + 8]) * s0);
+        a[2] = to_tf32(__half2float(D[(k0 + t + 4) * ldd + mrow0 + g]) * s1);
+        a[3] = to_tf32(__half2float(D[(k0 + t + 4) * ldd + mrow0 + g + 8]) * s1);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t b[2];
+            b[0] = __float_as_uint(__half2float(H[(k0 + t) * FIELD_LD + 8 * nt + g]));
+            b[1] = __float_as_uint(__half2float(H[(k0 + t + 4) * FIELD_LD + 8 * nt + g]));
+            mma1688_tf32(acc[nt], a, b);
+        }
+    }
+}
+
+#define FIELD_WGRAD_SMEM_BYTES (5 * 32 * FIELD_LD * 2 + 32 * FIELD_LD3 * 2 + 32 * 4)
+__global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_wgrad(FieldAct act, int64_t n, float *__restrict__ d_mlp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half *sX = reinterpret_cast<__half *>(smem_raw);
+    __half *sH1 = sX + 32 * FIELD_LD, *sH2 = sH1 + 32 * FIELD_LD, *sD2 = sH2 + 32 * FIELD_LD, *sD1 = sD2 + 32 * FIELD_LD;
+    __half *sDy = sD1 + 32 * FIELD_LD;
+    float *sS = reinterpret_cast<float *>(sDy + 32 * FIELD_LD3);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float a1[8][4], a2[8][4], a3[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a1[nt][k] = a2[nt][k] = a3[nt][k] = 0.f;
+    const int64_t n_tiles = (n + 31) / 32;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * 32;
+        __syncthreads();
+        // stage the five 32x64 tiles (+ dy^, s) with coalesced 16-byte loads: 5 * 256 vectors over 128 threads
+        for (int v = threadIdx.x; v < 5 * 256; v += IRIS_BLOCK) {
+            const int which = v >> 8, r = (v & 255) >> 3, c = (v & 7) * 8;
+            const __half *src = which == 0 ? act.X : which == 1 ? act.h1 : which == 2 ? act.h2 : which == 3 ? act.dh2 : act.dh1;
+            __half *dst = which == 0 ? sX : which == 1 ? sH1 : which == 2 ? sH2 : which == 3 ? sD2 : sD1;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (row0 + r < n) val = *reinterpret_cast<const uint4 *>(src + (row0 + r) * 64 + c);
+            *reinterpret_cast<uint4 *>(dst + r * FIELD_LD + c) = val;
+        }
+        if (threadIdx.x < 64) {
+            const int r = threadIdx.x >> 1, c = (threadIdx.x & 1) * 8;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (row0 + r < n) val = *reinterpret_cast<const uint4 *>(act.dy + (row0 + r) * 16 + c);
+            *reinterpret_cast<uint4 *>(sDy + r * FIELD_LD3 + c) = val;
+        } else if (threadIdx.x < 96) {
+            const int r = threadIdx.x - 64;
+            sS[r] = row0 + r < n ? act.s[row0 + r] : 0.f;
+        }
+        __syncthreads();
+        wgrad_tile(sD1, FIELD_LD, sX, sS, 16 * warp, a1);     // dW1 rows [16w,16w+16)
+        wgrad_tile(sD2, FIELD_LD, sH1, sS, 16 * warp, a2);    // dW2
+        if (warp == 0) wgrad_tile(sDy, FIELD_LD3, sH2, sS, 0, a3);   // dW3 (16 rows)
+    }
+    // one atomic per weight per CTA
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int r = 16 * warp + g, c = 8 * nt + 2 * t;
+        atomicAdd(d_mlp + r * 64 + c, a1[nt][0]); atomicAdd(d_mlp + r * 64 + c + 1, a1[nt][1]);
+        atomicAdd(d_mlp + (r + 8) * 64 + c, a1[nt][2]); atomicAdd(d_mlp + (r + 8) * 64 + c + 1, a1[nt][3]);
+        atomicAdd(d_mlp + 4096 + r * 64 + c, a2[nt][0]); atomicAdd(d_mlp + 4096 + r * 64 + c + 1, a2[nt][1]);
+        atomicAdd(d_mlp + 4096 + (r + 8) * 64 + c, a2[nt][2]); atomicAdd(d_mlp + 4096 + (r + 8) * 64 + c + 1, a2[nt][3]);
+        if (warp == 0) {
+            atomicAdd(d_mlp + 8192 + g * 64 + c, a3[nt][0]); atomicAdd(d_mlp + 8192 + g * 64 + c + 1, a3[nt][1]);
+            atomicAdd(d_mlp + 8192 + (g + 8) * 64 + c, a3[nt][2]); atomicAdd(d_mlp + 8192 + (g + 8) * 64 + c + 1, a3[nt][3]);
+        }
+    }
+}

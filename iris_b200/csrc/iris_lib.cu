@@ -38,8 +38,8 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
-enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_COUNT };
-static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward"};
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad"};
 struct ProfSpan { int id; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
@@ -274,13 +274,59 @@ int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t 
     return launch_field(P, n, position, mat, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int iris_field_backward(const IrisShadeParams *, const float *, const float *, int64_t, float *, void *) {
-    return fail(IRIS_ERR_INVALID, "iris_field_backward: not built yet");
+#define FIELD_BWD_CHUNK (1ll << 20)
+static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *position, const float4 *r5, const float *d_mat, float *d_params,
+                              void *workspace, int64_t workspace_bytes, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
+        attr_done = true;
+    }
+    const int64_t chunk = std::min<int64_t>(n, FIELD_BWD_CHUNK);
+    if (workspace_bytes < chunk * FIELD_ACT_BYTES_PER_SAMPLE) return fail(IRIS_ERR_WORKSPACE, "field backward: workspace too small");
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, n - c0);
+        FieldAct act = field_act_carve(workspace, m);
+        const int64_t tiles = (m + IRIS_BLOCK - 1) / IRIS_BLOCK;
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 3);
+        {
+            ProfScope ps(K_FIELD_BACKWARD, st);
+            if (r5) k_field_backward_dgrad<true><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act, d_params + 9216);
+            else k_field_backward_dgrad<false><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act, d_params + 9216);
+        }
+        LAUNCHED();
+        {
+            ProfScope ps(K_FIELD_WGRAD, st);
+            const unsigned g2 = (unsigned)std::min<int64_t>((m + 31) / 32, (int64_t)g_sm_count * 4);
+            k_field_backward_wgrad<<<g2, IRIS_BLOCK, FIELD_WGRAD_SMEM_BYTES, st>>>(act, m, d_params);
+        }
+        LAUNCHED();
+    }
+    return IRIS_OK;
+}
+
+int64_t iris_field_backward_workspace_bytes(int64_t n) { return std::min<int64_t>(std::max<int64_t>(n, 1), FIELD_BWD_CHUNK) * FIELD_ACT_BYTES_PER_SAMPLE; }
+
+int iris_field_backward(const IrisShadeParams *P, const float *position, const float *d_mat, int64_t n, float *d_params, void *workspace,
+                        int64_t workspace_bytes, void *stream) {
+    if (!P || !P->grid_f16 || !P->mlp_f16 || !(P->field_range > 0.f)) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
+    if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
+    if (n == 0) return IRIS_OK;
+    if (!position || !d_mat || !d_params || !workspace) return fail(IRIS_ERR_INVALID, "NULL array");
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(IRIS_ERR_INVALID, "workspace must be 16-byte aligned");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ensure_device_setup(dev);
+    if (rc) return rc;
+    return run_field_backward(P, n, position, nullptr, d_mat, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {
     const int64_t n = n_pixels * (int64_t)spp;
-    return 3 * 16 * n + 5 * 4 * n;   // w0,w1,w2 (forward) | d_mat (backward)
+    const int64_t fwd = 3 * 16 * n;                                                  // w0,w1,w2
+    const int64_t bwd = ((5 * 4 * n + 15) / 16) * 16 + iris_field_backward_workspace_bytes(n);   // d_mat | activation streams of one chunk
+    return std::max(fwd, bwd);
 }
 int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp) { return 6 * 16 * n_pixels * (int64_t)spp; }
 
@@ -319,17 +365,32 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
     if (n_pixels < 0 || spp <= 0) return fail(IRIS_ERR_INVALID, "bad arguments");
     if (n_pixels == 0) return IRIS_OK;
     if (!dL || !record) return fail(IRIS_ERR_INVALID, "NULL array");
-    if (d_params) return fail(IRIS_ERR_INVALID, "BRDF-field adjoint: not built yet");
-    (void)workspace;
-    (void)workspace_bytes;
     cudaStream_t st = (cudaStream_t)stream;
     const int K = P->n_emitters;
     const size_t smem = K <= IRIS_BWD_KMAX ? (size_t)3 * K * IRIS_BLOCK * 4 : 0;
     const int64_t n = n_pixels * spp;
+    float *d_mat = nullptr;
+    if (d_params) {
+        if (!P->grid_f16 || !P->mlp_f16) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
+        if (!workspace || workspace_bytes < iris_single_workspace_bytes(n_pixels, spp)) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
+    }
+    if (workspace) {   // d_mat (n,5) = J^T g is left at the start of the workspace (also without d_params, for inspection)
+        if (workspace_bytes < 5 * 4 * n) return fail(IRIS_ERR_WORKSPACE, "workspace too small for d_mat");
+        if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(IRIS_ERR_INVALID, "workspace must be 16-byte aligned");
+        d_mat = reinterpret_cast<float *>(workspace);
+    }
+    if (!d_radiance && !d_mat) return IRIS_OK;
     const unsigned grid = (unsigned)std::min<int64_t>(blocks_for(n), (int64_t)g_sm_count * 8);
-    ProfScope ps(K_SINGLE_BACKWARD, st);
-    k_single_backward<<<grid, IRIS_BLOCK, smem, st>>>(dL, n_pixels, spp, reinterpret_cast<const float4 *>(record), K, d_radiance, nullptr);
+    {
+        ProfScope ps(K_SINGLE_BACKWARD, st);
+        k_single_backward<<<grid, IRIS_BLOCK, d_radiance ? smem : 0, st>>>(dL, n_pixels, spp, reinterpret_cast<const float4 *>(record), K, d_radiance, d_mat);
+    }
     LAUNCHED();
+    if (d_params) {
+        const int64_t off = ((5 * 4 * n + 15) / 16) * 16;
+        return run_field_backward(P, n, nullptr, reinterpret_cast<const float4 *>(record) + 5 * n, d_mat, d_params,
+                                  reinterpret_cast<unsigned char *>(workspace) + off, workspace_bytes - off, st);
+    }
     return IRIS_OK;
 }
 

@@ -108,8 +108,7 @@ __device__ __forceinline__ f3 camera_dir(const float *__restrict__ rays, int64_t
     const float du = xsub(u0, 0.5f), dv = xsub(u1, 0.5f);
     const f3 v = mk3(xadd(xadd(r[3], xmul(r[6], du)), xmul(r[9], dv)), xadd(xadd(r[4], xmul(r[7], du)), xmul(r[10], dv)),
                      xadd(xadd(r[5], xmul(r[8], du)), xmul(r[11], dv)));
-    const float l = fmaxf(__fsqrt_rn(xadd(xadd(xmul(v.x, v.x), xmul(v.y, v.y)), xmul(v.z, v.z))), 1e-12f);
-    return mk3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
+    return normalize_nf(v);
 }
 
 __global__ void __launch_bounds__(IRIS_BLOCK) k_primary(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
 __global__ void __launch_bounds__(IRIS_BLOCK) k_single_backward(const float *__restrict__ dL, int64_t n_pixels, int spp,
                                                                  const float4 *__restrict__ rec, int K, float *d_radiance, float *d_mat) {
     extern __shared__ float acc[];   // [K*3][IRIS_BLOCK] when K <= IRIS_BWD_KMAX
-    const bool priv = K <= IRIS_BWD_KMAX;
+    const bool priv = K <= IRIS_BWD_KMAX && d_radiance != nullptr;
     const int tid = threadIdx.x;
     if (priv)
         for (int r = 0; r < 3 * K; ++r) acc[r * IRIS_BLOCK + tid] = 0.f;

@@ -83,9 +83,7 @@ struct Angles {
 };
 __device__ __forceinline__ Angles angles(f3 wi, f3 wo, f3 n) {
     // one rounding per op (the ATen chain of model/brdf.py:151-155): NoH feeds the ill-conditioned GGX denominator
-    const f3 s = mk3(xadd(wi.x, wo.x), xadd(wi.y, wo.y), xadd(wi.z, wo.z));
-    const float l = fmaxf(__fsqrt_rn(xdot(s, s)), 1e-12f);
-    const f3 h = mk3(__fdiv_rn(s.x, l), __fdiv_rn(s.y, l), __fdiv_rn(s.z, l));
+    const f3 h = normalize_nf(mk3(xadd(wi.x, wo.x), xadd(wi.y, wo.y), xadd(wi.z, wo.z)));
     Angles a;
     a.NoL = fmaxf(xdot(wi, n), 0.f);
     a.NoV = fmaxf(xdot(wo, n), 0.f);

@@ -224,12 +224,11 @@ def test_c1_forward_backward_golden():
     tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(c["H"]), c["params"], sc.voxel_bounds())
     U = torch.as_tensor(c["U"][:, :8]).to(dev)
     L, rec = core.single_forward(scene, tables, torch.as_tensor(c["rays"]).to(dev), c["spp"], core.Sampler(U=U), True)
-    # per pixel 16 samples x (3 rays + fp16-rounded material): one half-ulp flip of an fp16 rounding point (MLP accumulation
-    # order differs between tensor cores and the CPU GEMM) moves a channel by up to 9.8e-4 relative, so ~0.5% of pixels sit
-    # just above 1e-3; geometric flips (edge / voxel crossings) are rarer and larger
+    # Directions are normalised with the reference's own arithmetic (fma-chain norm, IEEE division), so primary hits are bit
+    # identical and what remains are isolated fp16 rounding-point flips of the field (MLP accumulation order on tensor cores).
     frac, worst = _frac_close(L.cpu().numpy(), g["L"])
     frac3, _ = _frac_close(L.cpu().numpy(), g["L"], rtol=3e-3)
-    assert frac >= 0.99 and frac3 >= 0.997, (frac, frac3, worst)
+    assert frac >= 0.998 and frac3 >= 0.9995, (frac, frac3, worst)
     d_rad = core.single_backward(tables, torch.as_tensor(c["Gw"]).to(dev), c["spp"], rec).cpu().numpy()
     frac, worst = _frac_close(d_rad, g["d_radiance"], rtol=2e-3)
     assert frac == 1.0, (d_rad, g["d_radiance"])
@@ -249,3 +248,98 @@ def test_single_production_stream_matches_oracle(small):
         ref = E.path_tracing_single(small["osc"], small["em"], small["mat_fn"], rays[:, 0:3], rays[:, 3:6], rays[:, 6:9], rays[:, 9:12], spp, U)
     frac, worst = _frac_close(L.cpu().numpy(), ref.numpy())
     assert frac >= 0.99, (frac, worst)
+
+
+def test_field_backward_matches_oracle(small):
+    """Adjoint of the BRDF field against torch autograd of the oracle restatement (straight-through fp16, fp32 gradients)."""
+    from iris_b200 import core
+    from oracle import field as OF
+    sc = small["sc"]
+    rng = np.random.default_rng(8)
+    lo, hi = sc.vertices.min(0), sc.vertices.max(0)
+    n = 3000                                                          # ragged: not a multiple of 32
+    x = torch.as_tensor((lo + (hi - lo) * rng.uniform(0, 1, (n, 3))).astype(np.float32))
+    dmat = torch.as_tensor((rng.standard_normal((n, 5)) * np.exp(rng.uniform(-12, 0, (n, 1)))).astype(np.float32))   # 5 decades of magnitudes
+    dmat[::7] = 0.0                                                   # lanes without gradient
+    vmin, vmax = sc.voxel_bounds()
+    p = small["params"].clone().requires_grad_(True)
+    m = OF.material(x, p, vmin, vmax)
+    (torch.cat([m["albedo"], m["roughness"], m["metallic"]], 1) * dmat).sum().backward()
+    ref = p.grad.numpy()
+    got = core.field_backward(small["tables"], x.to(small["dev"]), dmat.to(small["dev"])).cpu().numpy()
+    for name, sl in (("W1", slice(0, 4096)), ("W2", slice(4096, 8192)), ("W3", slice(8192, 9216)), ("grid", slice(9216, None))):
+        a, b = got[sl], ref[sl]
+        scale = np.abs(b).max()
+        assert scale > 0
+        err = np.abs(a - b).max() / scale
+        assert err < 2e-3, (name, err)
+    nz = np.nonzero(ref[9216:])[0]
+    assert np.array_equal(np.nonzero(got[9216:])[0], nz) or len(np.setxor1d(np.nonzero(got[9216:])[0], nz)) < 1e-3 * len(nz)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_single_backward_brdf_golden(name):
+    """path_tracing_single adjoint to the BRDF field parameters against the reference's own autograd (golden vectors; the
+    reference differentiates the fp16 sigmoid in fp16, hence 3e-3 of the largest entry)."""
+    dev = _gpu()
+    from iris_b200 import core
+    c = cases.build(name)
+    sc = c["sc"]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    scene = core.Scene(sc.vertices, sc.faces, 0)
+    tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(c["H"]), c["params"], sc.voxel_bounds())
+    U = torch.as_tensor(c["U"][:, :8]).to(dev)
+    L, rec = core.single_forward(scene, tables, torch.as_tensor(c["rays"]).to(dev), c["spp"], core.Sampler(U=U), True)
+    d_params = torch.zeros(c["params"].numel(), device=dev)
+    d_rad = core.single_backward(tables, torch.as_tensor(c["Gw"]).to(dev), c["spp"], rec, True, d_params)
+    frac, worst = _frac_close(d_rad.cpu().numpy(), g["d_radiance"], rtol=2e-3)
+    assert frac == 1.0
+    gp = d_params.cpu().numpy()
+    assert np.isfinite(gp).all()
+    # 3e-3 of the largest entry: the reference differentiates the fp16 sigmoid in fp16 (2-4e-4), the adjoint runs its dgrad on
+    # per-sample normalised fp16 / TF32 tensor-core operands (3-5e-4).  NOTE the finest hash levels have cells of 4e-5 scene
+    # units, so the gradient is only reproducible because hit points are bit-identical to the oracle's (see DESIGN.md).
+    tol = 3e-3
+    scale = np.abs(g["d_mlp"]).max()
+    assert np.abs(gp[:9216] - g["d_mlp"]).max() <= tol * scale, np.abs(gp[:9216] - g["d_mlp"]).max() / scale
+    lv_sum, lv_abs, top_i, top_v = cases.grid_fingerprint(gp[9216:])
+    assert np.allclose(lv_abs, g["d_grid_level_abs"], rtol=4 * tol), np.abs(lv_abs / g["d_grid_level_abs"] - 1).max()
+    gv = gp[9216:][g["d_grid_top_idx"]]
+    bad = np.abs(gv - g["d_grid_top_val"]) > 2 * tol * np.abs(g["d_grid_top_val"]).max()
+    assert bad.mean() < 0.005, bad.mean()
+
+
+def test_single_backward_dmat_per_lane(small):
+    """Per-sample Jacobian of path_tracing_single wrt (albedo, roughness, metallic): the adjoint's d_mat = J^T g against torch
+    autograd of the oracle, lane by lane (lanes whose forward radiance already differs -- geometric flips -- are excluded)."""
+    from iris_b200 import core
+    from oracle import estimators as E
+    dev, spp = small["dev"], small["spp"]
+    r = torch.as_tensor(small["rays"])
+    U = torch.as_tensor(small["U"][:, :8])
+    n = len(r) * spp
+    # oracle: material values as leaves so that .grad is the per-lane d_mat
+    leaves = {}
+
+    def mat_leaf(x):
+        m = small["mat_fn"](x)
+        if not leaves:
+            for k, v in m.items():
+                leaves[k] = v.detach().clone().requires_grad_(True)
+            return leaves
+        return {k: v.detach() for k, v in m.items()}
+    Lo, *_ = E._first_bounce(small["osc"], small["em"], mat_leaf, r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], spp, U, 0.0, True)
+    Gl = torch.as_tensor(np.random.default_rng(3).standard_normal((n, 3)).astype(np.float32))
+    (Lo * Gl).sum().backward()
+    ref = torch.cat([leaves["albedo"].grad, leaves["roughness"].grad, leaves["metallic"].grad], 1).numpy()
+    # CUDA: one lane per "pixel" (spp = 1) so that dL can be given per lane
+    rl = r.repeat_interleave(spp, 0).to(dev)
+    Lg, rec = core.single_forward(small["scene"], small["tables"], rl, 1, core.Sampler(U=U.to(dev)), True)
+    ws = torch.zeros(core.C.lib().iris_single_workspace_bytes(n, 1), dtype=torch.uint8, device=dev)
+    core.single_backward(small["tables"], Gl.to(dev), 1, rec, False, None, ws)
+    got = ws[:20 * n].view(torch.float32).reshape(n, 5).cpu().numpy()
+    same = (np.abs(Lg.cpu().numpy() - Lo.detach().numpy()) <= 2e-3 * np.maximum(np.abs(Lo.detach().numpy()), 1e-4)).all(1)
+    assert same.mean() > 0.98
+    scale = np.abs(ref[same]).max(0)
+    err = np.abs(got[same] - ref[same]) / np.maximum(np.abs(ref[same]), 1e-3 * scale)
+    assert (err < 5e-3).mean() > 0.995, ((err < 5e-3).mean(), err.max())

@@ -33,7 +33,22 @@ print("primary prim mismatch (same rays)", int((prim.cpu().long() != tri0).sum()
 idx = torch.nonzero(bad)[:, 0]
 big = err.max(1).values
 print("err quantiles over bad lanes", np.quantile(big[idx].numpy(), [0.1, 0.5, 0.9]) if len(idx) else None)
-for i in idx[:12].tolist():
+# split of the oracle radiance: direct emission / NEE / BSDF
+with torch.no_grad():
+    position, normal, _, tri, _ = osc.ray_intersect(o, wi0)
+    L0, _, active = em.eval_emitter(position, tri)
+    position_s, normal_s, wo_s = E._sanitize(active, position, normal, -wi0)
+    mat = mat_fn(position_s)
+    Lnee = torch.where(active[:, None], E._nee(osc, em, mat, position_s, normal_s, wo_s, U[:, 2], U[:, 3:5], active, 1e-6, True), torch.zeros_like(L0))
+    wi_b, bpdf, bw = E.sample_brdf(U[:, 5], U[:, 6:8], wo_s, normal_s, mat)
+    pn, nn2, _, tri_b, _ = osc.ray_intersect(position_s + E.RAY_EPSILON * wi_b, wi_b)
+Lb = Lo - L0 - Lnee
+order = torch.argsort(-big)[:14]
+print("largest-error lanes: lane err | gpu | oracle | L0 | Lnee | Lbsdf | u_lobe roughness tri_b t-ish")
+for i in order.tolist():
+    print(i, round(float(big[i]), 4), Lg[i].numpy().round(5), Lo[i].numpy().round(5), L0[i].numpy().round(4), Lnee[i].numpy().round(5), Lb[i].numpy().round(5),
+          round(float(U[i, 5]), 4), round(float(mat["roughness"][i]), 4), int(tri_b[i]), "diffG-O", (Lg[i] - Lo[i]).numpy().round(5))
+for i in idx[:4].tolist():
     print(i, "gpu", Lg[i].numpy(), "oracle", Lo[i].numpy(), "U", U[i].numpy().round(4))
 # material parity at the oracle's primary hits
 pos, nrm, _, tri, _ = osc.ray_intersect(o, wi0)
