@@ -159,12 +159,31 @@ int iris_single_backward(const IrisShadeParams *params, const float *dL, int64_t
                          const void *record, float *d_radiance, float *d_params,
                          void *workspace, int64_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Forward-only estimators that evaluate the BRDF field at every hit (wavefront: trace -> field -> shade per bounce).
+ *   iris_path_tracing      path_tracing(..., spp, indir_depth)            utils/path_tracing.py:214-318  (render.py:171-176)
+ *   iris_path_tracing_det  path_tracing_det_diff (mode 0) / _det_spec (1) utils/path_tracing.py:50-212   (refine_shading.py:116-122,160-166)
+ *                          positions/wis/normals (B,3), prim (B) int32 with -1 = pixel without a hit -> zeros; mode 1 also writes L1
+ *   iris_trace_indirect    trace_indirect(position, wo, normal, depth)    utils/path_tracing.py:409-502  -> L (n,3) per lane
+ * Sampler columns: path_tracing 0 du,1 dv,2..7 first bounce, then 6 per indirect depth (e1,e2x,e2y,b1,b2x,b2y); det: 0..1 first sample,
+ * then 6 per depth; trace_indirect: 6 per depth from column 0.  workspace >= iris_wave_workspace_bytes(lanes), lanes = rows * spp.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t iris_wave_workspace_bytes(int64_t n_lanes);
+int iris_path_tracing(const IrisScene *scene, const IrisShadeParams *params, const float *rays, int64_t n_pixels, int32_t spp,
+                      int32_t indir_depth, const IrisSampler *sampler, float *L, void *workspace, int64_t workspace_bytes, void *stream);
+int iris_path_tracing_det(const IrisScene *scene, const IrisShadeParams *params, int mode, float roughness_level, const float *positions,
+                          const float *wis, const float *normals, const int32_t *prim, int64_t n_pixels, int32_t spp, int32_t indir_depth,
+                          const IrisSampler *sampler, float *L0, float *L1, void *workspace, int64_t workspace_bytes, void *stream);
+int iris_trace_indirect(const IrisScene *scene, const IrisShadeParams *params, const float *position, const float *wo, const float *normal,
+                        int64_t n, int32_t indir_depth, const IrisSampler *sampler, float *L, void *workspace, int64_t workspace_bytes,
+                        void *stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t iris_launch_count(void);
 
 /* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its own stream.
  * iris_profile_read synchronises the pending events and returns the launch count and the summed duration of one
- * kernel class (ids 0..8, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */
+ * kernel class (ids 0..12, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */
 int iris_profile_enable(int on);
 const char *iris_profile_name(int kernel_id);
 int iris_profile_read(int kernel_id, int64_t *launches, double *total_ms, int reset);

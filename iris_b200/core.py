@@ -255,3 +255,52 @@ def single_backward(tables, dL, spp, record, want_radiance=True, d_params=None, 
         C.check(lib.iris_single_backward(ctypes.byref(P), C.ptr(dL), B, int(spp), C.ptr(record), C.ptr(d_rad), C.ptr(d_params),
                                          C.ptr(workspace), 0 if workspace is None else workspace.numel(), C.stream_ptr()))
     return d_rad
+
+
+def _wave_ws(n_lanes, dev, workspace):
+    wb = C.lib().iris_wave_workspace_bytes(n_lanes)
+    if workspace is None or workspace.numel() < wb:
+        workspace = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
+    return workspace
+
+
+def path_tracing(scene, tables, rays, spp, indir_depth, sampler, workspace=None):
+    """path_tracing (utils/path_tracing.py:214-318), forward only: L (B,3)."""
+    rays = rays.contiguous().float()
+    B, dev = rays.shape[0], rays.device
+    L = torch.empty(B, 3, device=dev)
+    ws = _wave_ws(B * int(spp), dev, workspace)
+    P, S = tables.c(), sampler.c()
+    with torch.cuda.device(dev):
+        C.check(C.lib().iris_path_tracing(scene.handle, ctypes.byref(P), C.ptr(rays), B, int(spp), int(indir_depth), ctypes.byref(S), C.ptr(L),
+                                          C.ptr(ws), ws.numel(), C.stream_ptr()))
+    return L
+
+
+def path_tracing_det(scene, tables, mode, roughness_level, positions, wis, normals, prim, spp, indir_depth, sampler, workspace=None):
+    """path_tracing_det_diff (mode 0) -> L ; path_tracing_det_spec (mode 1) -> (L0, L1)   (utils/path_tracing.py:50-212)."""
+    positions, wis, normals = positions.contiguous().float(), wis.contiguous().float(), normals.contiguous().float()
+    prim = prim.to(torch.int32).contiguous()
+    B, dev = positions.shape[0], positions.device
+    L0 = torch.empty(B, 3, device=dev)
+    L1 = torch.empty(B, 3, device=dev) if mode == 1 else None
+    ws = _wave_ws(B * int(spp), dev, workspace)
+    P, S = tables.c(), sampler.c()
+    with torch.cuda.device(dev):
+        C.check(C.lib().iris_path_tracing_det(scene.handle, ctypes.byref(P), mode, float(roughness_level), C.ptr(positions), C.ptr(wis), C.ptr(normals),
+                                              C.ptr(prim), B, int(spp), int(indir_depth), ctypes.byref(S), C.ptr(L0), C.ptr(L1), C.ptr(ws), ws.numel(),
+                                              C.stream_ptr()))
+    return L0 if mode == 0 else (L0, L1)
+
+
+def trace_indirect(scene, tables, position, wo, normal, indir_depth, sampler, workspace=None):
+    """trace_indirect (utils/path_tracing.py:409-502): L (n,3)."""
+    position, wo, normal = position.contiguous().float(), wo.contiguous().float(), normal.contiguous().float()
+    n, dev = position.shape[0], position.device
+    L = torch.zeros(n, 3, device=dev)
+    ws = _wave_ws(n, dev, workspace)
+    P, S = tables.c(), sampler.c()
+    with torch.cuda.device(dev):
+        C.check(C.lib().iris_trace_indirect(scene.handle, ctypes.byref(P), C.ptr(position), C.ptr(wo), C.ptr(normal), n, int(indir_depth), ctypes.byref(S),
+                                            C.ptr(L), C.ptr(ws), ws.numel(), C.stream_ptr()))
+    return L

@@ -10,6 +10,7 @@
 #include "bvh8.h"
 #include "field.cuh"
 #include "kernels.cuh"
+#include "wavefront.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -38,8 +39,8 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
-enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_COUNT };
-static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad"};
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish"};
 struct ProfSpan { int id; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
@@ -391,6 +392,143 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
         return run_field_backward(P, n, nullptr, reinterpret_cast<const float4 *>(record) + 5 * n, d_mat, d_params,
                                   reinterpret_cast<unsigned char *>(workspace) + off, workspace_bytes - off, st);
     }
+    return IRIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ wavefront estimators
+int64_t iris_wave_workspace_bytes(int64_t n_lanes) { return WAVE_STREAMS * 16 * std::max<int64_t>(n_lanes, 1); }
+
+static int wave_field(const IrisShadeParams *P, int64_t n, float4 *pos, float4 *m1, float4 *m2, cudaStream_t st) {
+    return launch_field(P, n, nullptr, nullptr, pos, m1, m2, st);
+}
+
+// one indirect depth (trace_indirect loop body) on the current state
+static int wave_indirect(const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int64_t n, WaveState W, int depth, int col_base,
+                         cudaStream_t st) {
+    for (int k = 0; k < depth; ++k) {
+        {
+            ProfScope ps(K_WAVE_A, st);
+            k_wave_bounce_a<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, col_base + 6 * k, 0.f, n, W);
+        }
+        LAUNCHED();
+        int rc = wave_field(P, n, W.H0, W.M1, W.M2, st);
+        if (rc) return rc;
+        {
+            ProfScope ps(K_WAVE_B, st);
+            k_wave_bounce_b<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W);
+        }
+        LAUNCHED();
+    }
+    return IRIS_OK;
+}
+
+static int wave_check(const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int64_t n_rows, int32_t spp, int32_t depth, int need_cols,
+                      void *ws, int64_t ws_bytes) {
+    if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
+    int rc = check_params(P, true);
+    if (rc) return rc;
+    if (n_rows < 0 || spp <= 0 || depth < 0 || !smp) return fail(IRIS_ERR_INVALID, "bad arguments");
+    if (smp->U && smp->stride < need_cols) return fail(IRIS_ERR_INVALID, "sampler stride too small for this estimator / depth");
+    if (n_rows > 0 && (!ws || ws_bytes < iris_wave_workspace_bytes(n_rows * spp))) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(IRIS_ERR_INVALID, "workspace must be 16-byte aligned");
+    return IRIS_OK;
+}
+
+int iris_path_tracing(const IrisScene *s, const IrisShadeParams *P, const float *rays, int64_t n_pixels, int32_t spp, int32_t indir_depth,
+                      const IrisSampler *smp, float *L, void *workspace, int64_t workspace_bytes, void *stream) {
+    int rc = wave_check(s, P, smp, n_pixels, spp, indir_depth, 8 + 6 * indir_depth, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (n_pixels == 0) return IRIS_OK;
+    if (!rays || !L) return fail(IRIS_ERR_INVALID, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_pixels * spp;
+    WaveState W = wave_carve(workspace, n);
+    CUDA_TRY(cudaMemsetAsync(L, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    {
+        ProfScope ps(K_WAVE_INIT, st);
+        k_wave_init_camera<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, rays, n_pixels, spp, W);
+    }
+    LAUNCHED();
+    if ((rc = wave_field(P, n, W.S0, W.S1, W.S2, st))) return rc;
+    {
+        ProfScope ps(K_WAVE_A, st);
+        k_wave_bounce_a<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, 2, 0.f, n, W);
+    }
+    LAUNCHED();
+    if ((rc = wave_field(P, n, W.H0, W.M1, W.M2, st))) return rc;
+    {
+        ProfScope ps(K_WAVE_B, st);
+        k_wave_bounce_b<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W);
+    }
+    LAUNCHED();
+    if ((rc = wave_indirect(s, P, smp, n, W, indir_depth, 8, st))) return rc;
+    {
+        ProfScope ps(K_WAVE_FINISH, st);
+        k_wave_finish<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n_pixels, spp, W, L, nullptr);
+    }
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_path_tracing_det(const IrisScene *s, const IrisShadeParams *P, int mode, float roughness_level, const float *positions, const float *wis,
+                          const float *normals, const int32_t *prim, int64_t n_pixels, int32_t spp, int32_t indir_depth, const IrisSampler *smp,
+                          float *L0, float *L1, void *workspace, int64_t workspace_bytes, void *stream) {
+    int rc = wave_check(s, P, smp, n_pixels, spp, indir_depth, 2 + 6 * indir_depth, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (mode != 0 && mode != 1) return fail(IRIS_ERR_INVALID, "mode must be 0 (diffuse) or 1 (specular)");
+    if (n_pixels == 0) return IRIS_OK;
+    if (!positions || !wis || !normals || !prim || !L0 || (mode == 1 && !L1)) return fail(IRIS_ERR_INVALID, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_pixels * spp;
+    WaveState W = wave_carve(workspace, n);
+    CUDA_TRY(cudaMemsetAsync(L0, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    if (mode == 1) CUDA_TRY(cudaMemsetAsync(L1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    {
+        ProfScope ps(K_WAVE_INIT, st);
+        k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(positions, wis, 1, normals, prim, n_pixels, spp, W);
+    }
+    LAUNCHED();
+    {
+        ProfScope ps(K_WAVE_A, st);
+        if (mode == 0) k_wave_bounce_a<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, 0, 0.f, n, W);
+        else k_wave_bounce_a<3><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, 0, roughness_level, n, W);
+    }
+    LAUNCHED();
+    if ((rc = wave_field(P, n, W.H0, W.M1, W.M2, st))) return rc;
+    {
+        ProfScope ps(K_WAVE_B, st);
+        k_wave_bounce_b<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W);
+    }
+    LAUNCHED();
+    if ((rc = wave_indirect(s, P, smp, n, W, indir_depth, 2, st))) return rc;
+    {
+        ProfScope ps(K_WAVE_FINISH, st);
+        k_wave_finish<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n_pixels, spp, W, L0, mode == 1 ? L1 : nullptr);
+    }
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_trace_indirect(const IrisScene *s, const IrisShadeParams *P, const float *position, const float *wo, const float *normal, int64_t n,
+                        int32_t indir_depth, const IrisSampler *smp, float *L, void *workspace, int64_t workspace_bytes, void *stream) {
+    int rc = wave_check(s, P, smp, n, 1, indir_depth, 6 * indir_depth, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (n == 0) return IRIS_OK;
+    if (!position || !wo || !normal || !L) return fail(IRIS_ERR_INVALID, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    WaveState W = wave_carve(workspace, n);
+    {
+        ProfScope ps(K_WAVE_INIT, st);
+        k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(position, wo, 0, normal, nullptr, n, 1, W);
+    }
+    LAUNCHED();
+    if ((rc = wave_field(P, n, W.S0, W.S1, W.S2, st))) return rc;
+    if ((rc = wave_indirect(s, P, smp, n, W, indir_depth, 0, st))) return rc;
+    {
+        ProfScope ps(K_WAVE_FINISH, st);
+        k_wave_finish<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n, 1, W, L, nullptr);
+    }
+    LAUNCHED();
     return IRIS_OK;
 }
 

@@ -1,0 +1,203 @@
+"""Operator layer: the reference's call surface on top of the C ABI.
+
+ * `tables_for(emitter_net, material_net)` builds (and caches on the modules) the device tables the kernels read, from ANY
+   object that carries the reference's buffers -- the reference's own `SLFEmitter` / `NGPBRDF` instances or the mirrors in
+   `iris_b200.model` (duck typing on `is_emitter`, `emitter_vertices`, `emitter_area`, `radiance`, `slf.inds`, `slf.radiance`,
+   `slf.voxel_min/max`, `mlp.params`, `voxel_min/max`).
+ * `PathTracingSingle` is the `torch.autograd.Function` that ties `iris_single_forward` to `iris_single_backward`: gradients
+   flow to `emitter_net.radiance` (rows [0,K), the reference's quirk) and to `material_net.mlp.params`.
+ * uniforms: Philox keyed by a seed drawn from torch's global generator per call (reproducible under `torch.manual_seed`,
+   like the reference's `torch.rand`), or an explicit `(N,D)` buffer via `iris_b200.ops.inject_samples(U)` for parity runs.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi as C
+from . import core
+
+_INJECT = []
+
+
+@contextlib.contextmanager
+def inject_samples(U):
+    """Run the estimators inside with the explicit (N,D) uniform buffer U (identical injected sequences)."""
+    _INJECT.append(U)
+    try:
+        yield
+    finally:
+        _INJECT.pop()
+
+
+def next_sampler(device):
+    if _INJECT:
+        return core.Sampler(U=_INJECT[-1].to(device))
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # advances torch's global generator like torch.rand would
+    return core.Sampler(seed=seed)
+
+
+# ------------------------------------------------------------------------------------------------ scene handle
+def as_scene(scene):
+    """Accept an iris_b200.core.Scene, or the object returned by the mitsuba compat shim's load_dict."""
+    if isinstance(scene, core.Scene):
+        return scene
+    s = getattr(scene, "iris_scene", None)
+    if s is None:
+        raise TypeError("scene must be an iris_b200 Scene (use iris_b200.compat.mitsuba.load_dict or iris_b200.core.Scene)")
+    return s
+
+
+# ------------------------------------------------------------------------------------------------ tables
+def _ver(t):
+    return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+
+
+def tables_for(emitter_net, material_net=None, device=None):
+    dev = torch.device(device) if device is not None else emitter_net.radiance.device
+    cache = emitter_net.__dict__.setdefault("_iris_cache", {})
+    T = cache.get("tables")
+    if T is None or T.device != dev:
+        T = core.ShadingTables(dev)
+        cache.clear()
+        cache["tables"] = T
+    key = (_ver(emitter_net.is_emitter), _ver(emitter_net.emitter_vertices), _ver(emitter_net.emitter_area))
+    if cache.get("emitter_key") != key:
+        T.set_emitter(emitter_net.is_emitter, emitter_net.emitter_vertices, emitter_net.emitter_area, emitter_net.radiance)
+        cache["emitter_key"] = key
+    r = emitter_net.radiance.detach()
+    T.t["radiance"] = r if (r.device == dev and r.dtype == torch.float32 and r.is_contiguous()) else r.to(dev, torch.float32).contiguous()
+    slf = emitter_net.slf
+    key = (_ver(slf.inds), _ver(slf.radiance), float(slf.voxel_min), float(slf.voxel_max))
+    if cache.get("slf_key") != key:
+        T.set_slf(slf.inds, slf.radiance, slf.voxel_min, slf.voxel_max)
+        cache["slf_key"] = key
+    if material_net is not None and hasattr(material_net, "mlp"):
+        p = material_net.mlp.params
+        key = (_ver(p), float(material_net.voxel_min), float(material_net.voxel_max))
+        if cache.get("field_key") != key:
+            T.set_field(p, material_net.voxel_min, material_net.voxel_max)
+            cache["field_key"] = key
+    return T
+
+
+# ------------------------------------------------------------------------------------------------ ray_intersect
+def ray_intersect(scene, xs, ds):
+    """utils/path_tracing.py:17-48: positions, normals (flipped toward -ds), uvs, idx (int64, -1 = miss), valid."""
+    sc = as_scene(scene)
+    shape = xs.shape[:-1]
+    t, prim, uv, p, n = sc.intersect_raw(xs.reshape(-1, 3), ds.reshape(-1, 3))
+    idx = prim.long()
+    return p.reshape(*shape, 3), n.reshape(*shape, 3), uv.reshape(*shape, 2), idx.reshape(shape), (idx >= 0).reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------------ path_tracing_single
+class PathTracingSingle(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, radiance, params, scene, tables, rays, spp, sampler):
+        need_rad = radiance is not None and radiance.requires_grad
+        need_par = params is not None and params.requires_grad
+        L, rec = core.single_forward(scene, tables, rays, spp, sampler, want_record=need_rad or need_par)
+        ctx.tables, ctx.spp, ctx.rec = tables, spp, rec
+        ctx.need = (need_rad, need_par)
+        ctx.shapes = (None if radiance is None else radiance.shape, None if params is None else params.shape)
+        return L
+
+    @staticmethod
+    def backward(ctx, dL):
+        need_rad, need_par = ctx.need
+        d_rad = d_par = None
+        if ctx.rec is not None and (need_rad or need_par):
+            if need_par:
+                d_par = torch.zeros(ctx.shapes[1], device=dL.device, dtype=torch.float32)
+            g = core.single_backward(ctx.tables, dL, ctx.spp, ctx.rec, want_radiance=need_rad, d_params=d_par)
+            if need_rad:
+                d_rad = torch.zeros(ctx.shapes[0], device=dL.device, dtype=torch.float32)      # (F,3): only rows [0,K) receive gradient
+                d_rad[:ctx.tables.K] = g
+        return d_rad, d_par, None, None, None, None, None
+
+
+def pack_rays(rays_o, rays_d, dx_du, dy_dv):
+    return torch.cat([rays_o, rays_d, dx_du, dy_dv], -1).float().contiguous()
+
+
+def path_tracing_single(scene, emitter_net, material_net, rays_o, rays_d, dx_du, dy_dv, spp):
+    """utils/path_tracing.py:320-407 as one fused forward (+ replay adjoint through autograd)."""
+    sc = as_scene(scene)
+    T = tables_for(emitter_net, material_net, rays_o.device)
+    params = material_net.mlp.params if hasattr(material_net, "mlp") else None
+    return PathTracingSingle.apply(emitter_net.radiance, params, sc, T, pack_rays(rays_o, rays_d, dx_du, dy_dv), int(spp), next_sampler(rays_o.device))
+
+
+def path_tracing(scene, emitter_net, material_net, rays_o, rays_d, dx_du, dy_dv, spp, indir_depth):
+    """utils/path_tracing.py:214-318.  Forward only: the reference itself calls it under no_grad (render.py:171-176,
+    train_brdf_crf.py:360-370) and detaches everything past the first bounce (:313-315)."""
+    T = tables_for(emitter_net, material_net, rays_o.device)
+    return core.path_tracing(as_scene(scene), T, pack_rays(rays_o, rays_d, dx_du, dy_dv), spp, indir_depth, next_sampler(rays_o.device))
+
+
+def path_tracing_det(scene, emitter_net, material_net, roughness_level, positions, wis, normals, triangle_idxs, spp, indir_depth):
+    """utils/path_tracing.py:50-124 (roughness_level None) and :127-212."""
+    T = tables_for(emitter_net, material_net, positions.device)
+    if positions.shape[0] == 0:
+        z = torch.zeros_like(positions)
+        return z if roughness_level is None else (z, z.clone())
+    mode = 0 if roughness_level is None else 1
+    return core.path_tracing_det(as_scene(scene), T, mode, 0.0 if roughness_level is None else float(roughness_level), positions, wis, normals,
+                                 triangle_idxs, spp, indir_depth, next_sampler(positions.device))
+
+
+def trace_indirect(scene, emitter_net, material_net, position, wo, normal, indir_depth):
+    """utils/path_tracing.py:409-502."""
+    T = tables_for(emitter_net, material_net, position.device)
+    if position.shape[0] == 0:
+        return torch.zeros_like(position)
+    return core.trace_indirect(as_scene(scene), T, position, wo, normal, indir_depth, next_sampler(position.device))
+
+
+# ------------------------------------------------------------------------------------------------ bake
+def bake_diffuse(scene, emitter_net, position, normal, spp):
+    """The chunk loop of bake_shading.py:105-123 as one launch: Ld (B,3)."""
+    T = tables_for(emitter_net, None, position.device)
+    return core.bake(as_scene(scene), T, 0, 1.0, position, normal, None, spp, next_sampler(position.device))
+
+
+def bake_specular(scene, emitter_net, position, wo, normal, roughness, spp):
+    """The chunk loop of bake_shading.py:165-188 for one roughness level: (Ls0, Ls1)."""
+    T = tables_for(emitter_net, None, position.device)
+    return core.bake(as_scene(scene), T, 1, float(roughness), position, normal, wo, spp, next_sampler(position.device))
+
+
+# ------------------------------------------------------------------------------------------------ BRDF field
+class FieldForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, tables, position):
+        ctx.tables = tables
+        ctx.save_for_backward(position)
+        ctx.n_params = params.numel()
+        return core.field_forward(tables, position)
+
+    @staticmethod
+    def backward(ctx, d_mat):
+        (position,) = ctx.saved_tensors
+        d = torch.zeros(ctx.n_params, device=d_mat.device, dtype=torch.float32)
+        core.field_backward(ctx.tables, position, d_mat, d)
+        return d, None, None
+
+
+def field(material_net, position):
+    """NGPBRDF.forward (model/brdf.py:243-260): dict(albedo (N,3), roughness (N,1), metallic (N,1))."""
+    dev = position.device
+    cache = material_net.__dict__.setdefault("_iris_cache", {})
+    T = cache.get("tables")
+    p = material_net.mlp.params
+    key = (_ver(p), float(material_net.voxel_min), float(material_net.voxel_max))
+    if T is None or T.device != dev or cache.get("field_key") != key:
+        T = core.ShadingTables(dev).set_field(p, material_net.voxel_min, material_net.voxel_max)
+        cache["tables"], cache["field_key"] = T, key
+    shape = position.shape[:-1]
+    mat = FieldForward.apply(p, T, position.reshape(-1, 3).float().contiguous())
+    return {"albedo": mat[:, 0:3].reshape(*shape, 3), "roughness": mat[:, 3:4].reshape(*shape, 1), "metallic": mat[:, 4:5].reshape(*shape, 1)}
