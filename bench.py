@@ -5,9 +5,10 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
 
 A *step* = one pass of `path_tracing_single` forward + adjoint over one batch of synthetic camera rays:
-workload "c4" (default; BASELINE.json configs[3], the train_emitter.py step): 1M-triangle room, 8 views 1280x960 per GPU,
-SPP=256 as 8 chunks of spp=32, K=16 emitter triangles, MIS on, MSE loss, gradient to emitter.radiance; the scene/BVH, SLF and
-BRDF field are replicated, pixels are sharded by view, and the only collective is the allreduce of d_radiance.
+workload "c3" (default; BASELINE.json configs[2]): 1M-triangle room, 8 views 1280x960 per GPU, SPP=256 as 8 chunks of spp=32,
+random-init hash-grid+MLP BRDF field, K=16 emitter triangles, MIS on, MSE loss, gradients to the field parameters (27.96M) and
+to emitter.radiance ("c4" = configs[3]: emitter-radiance gradient only, the train_emitter.py step).  The scene/BVH, SLF and BRDF
+field are replicated, pixels are sharded by view, and the only collective is the allreduce of the flat gradient buffer.
 A *path sample* = one (pixel, spp index) lane through the whole estimator (3 ray casts, BRDF-field evaluation, emitter / SLF
 lookups, MIS, adjoint replay).
 
@@ -32,9 +33,11 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: tris, emitters, views per GPU, width, height, SPP, spp, estimator
-    "c4": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32,
+    "c3": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32, brdf_grad=True,
+               desc="training step: path_tracing_single fwd+bwd with gradients to the BRDF field (hash grid + MLP) AND emitter radiance, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), random-init field, K=16, MIS on"),
+    "c4": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32, brdf_grad=False,
                desc="train_emitter step: path_tracing_single fwd+bwd, emitter-radiance gradient, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), K=16, MIS on"),
-    "c1": dict(tris=10_000, emitters=2, views=1, width=64, height=64, SPP=16, spp=16,
+    "c1": dict(tris=10_000, emitters=2, views=1, width=64, height=64, SPP=16, spp=16, brdf_grad=True,
                desc="Cornell ~10k tris, 64x64, spp=16, path_tracing_single fwd+bwd (reference's CPU-runnable case)"),
 }
 
@@ -50,7 +53,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--views", type=int, default=None)
     ap.add_argument("--tile", type=int, default=262144, help="pixels per forward/backward tile")
     ap.add_argument("--cpu-sample-pixels", type=int, default=8192)
@@ -71,7 +74,7 @@ def cpu_leg(w, sc, n_pixels, steps, warmup):
     torch.set_num_threads(cores)
     osc = OracleScene(sc.vertices, sc.faces)
     em = E.Emitter(sc.emitter_dict(), sc.slf_dict(256), learn=True)
-    params = bench_params()
+    params = bench_params().requires_grad_(bool(w.get("brdf_grad")))
     vmin, vmax = sc.voxel_bounds()
     mat_fn = lambda x: OF.material(x, params, vmin, vmax)
     rays = torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=1))
@@ -86,13 +89,14 @@ def cpu_leg(w, sc, n_pixels, steps, warmup):
         L = E.path_tracing_single(osc, em, mat_fn, r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], spp, U)
         loss = ((L - 0.5) ** 2).mean()
         em.radiance.grad = None
+        params.grad = None
         loss.backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     per = float(np.mean(times))
     return dict(value=len(r) * spp / per, unit="samples/s", cores=cores, kind="port",
-                sample="%d pixels (every %d-th of view 1) x spp %d, one chunk, fwd+bwd to emitter.radiance" % (len(r), stride, spp)), per
+                sample="%d pixels (every %d-th of view 1) x spp %d, one chunk, fwd+bwd to %s" % (len(r), stride, spp, "field params + emitter.radiance" if w.get("brdf_grad") else "emitter.radiance")), per
 
 
 def bench_params():
@@ -187,6 +191,7 @@ def main():
 
     import torch
     from iris_b200 import core
+    from iris_b200 import dist as idist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -208,15 +213,20 @@ def main():
     spp = w["spp"]
     tile = min(a.tile, P)
     lib = core.C.lib()
-    ws = torch.empty(lib.iris_single_workspace_bytes(tile, spp), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.iris_single_workspace_bytes(tile, spp), dtype=torch.uint8, device=dev)   # forward streams | d_mat + activation streams
     recs = [torch.empty(lib.iris_single_record_bytes(tile, spp), dtype=torch.uint8, device=dev) for _ in range(n_chunks)]
     target = torch.full((P, 3), 0.5, device=dev)
     n_samples_rank = P * w["SPP"]
     step_no = [0]
 
+    want_par = bool(w.get("brdf_grad"))
+    d_par_buf = torch.zeros(9216 + 27954112, device=dev) if want_par else None
+
     def step(host_inputs):
         """One training step of this rank: returns (loss tensor, d_radiance)."""
         d_rad = torch.zeros(tables.K, 3, device=dev)
+        if want_par:
+            d_par_buf.zero_()
         loss = torch.zeros((), device=dev)
         s = step_no[0]
         step_no[0] += 1
@@ -237,14 +247,16 @@ def main():
             dL = diff * (2.0 / (P * 3 * world * n_chunks))
             for c in range(n_chunks):
                 P_ = tables.c()
-                core.C.check(lib.iris_single_backward(P_, core.C.ptr(dL), t1 - t0, spp, core.C.ptr(recs[c]), core.C.ptr(d_rad), None, None, 0,
-                                                      core.C.stream_ptr()))
+                core.C.check(lib.iris_single_backward(P_, core.C.ptr(dL), t1 - t0, spp, core.C.ptr(recs[c]), core.C.ptr(d_rad), core.C.ptr(d_par_buf),
+                                                      core.C.ptr(ws) if want_par else None, ws.numel() if want_par else 0, core.C.stream_ptr()))
         if dist is not None:
-            dist.all_reduce(d_rad)
+            idist.allreduce_gradients([d_rad, d_par_buf])
             dist.all_reduce(loss)
         if host_inputs:
-            return loss.cpu(), d_rad.cpu()
-        return loss, d_rad
+            # the optimiser consumes gradients on the device; what leaves the GPU per step is the loss, the K x 3 emitter gradient
+            # and (to make the field gradient observable) its L1 norm
+            return loss.cpu(), d_rad.cpu(), (d_par_buf.abs().sum().cpu() if want_par else None)
+        return loss, d_rad, (d_par_buf.abs().sum() if want_par else None)
 
     def barrier():
         if dist is not None:
@@ -271,13 +283,13 @@ def main():
     if rank == 0:
         clocks.start()
     lib.iris_profile_enable(1)
-    for k in range(8):
+    for k in range(14):
         lib.iris_profile_read(k, None, None, 1)
     l0 = lib.iris_launch_count()
-    ms, (loss, d_rad) = timed(False, a.steps)
+    ms, (loss, d_rad, d_par_l1) = timed(False, a.steps)
     launches = lib.iris_launch_count() - l0
     prof = {}
-    for k in range(8):
+    for k in range(14):
         n_, t_ = core.C.c_i64(), core.C.ctypes.c_double()
         lib.iris_profile_read(k, core.C.ctypes.byref(n_), core.C.ctypes.byref(t_), 1)
         if n_.value:
@@ -292,7 +304,7 @@ def main():
         step(True)
         ms_e, _ = timed(True, a.steps)
         e2e = dict(value=n_samples_rank * world * a.steps / (ms_e * 1e-3), unit="samples/s", h2d_bytes_per_step=int(P * 12 * 4 * world),
-                   d2h_bytes_per_step=int((tables.K * 3 + 1) * 4 * world), ms_per_step=ms_e / a.steps)
+                   d2h_bytes_per_step=int((tables.K * 3 + 2) * 4 * world), ms_per_step=ms_e / a.steps)
 
     if rank != 0:
         if dist is not None:
@@ -307,7 +319,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     R = ray_bytes(sc.n_tris)
-    est_bytes = 3 * R + 1024 + 16 + 72.0 / spp            # SURVEY 8d, emitter-gradient `single` estimator
+    est_bytes = 3 * R + (2048 if want_par else 1024) + 16 + 72.0 / spp      # `single` estimator (+1024 B of grid-gradient writes with BRDF grads)
     kb = prof.get("k_bounce_single")
     roof = None
     if kb:
@@ -334,7 +346,7 @@ def main():
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cb,
                 scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
-                loss=float(loss), d_radiance_abs_sum=float(d_rad.abs().sum()))
+                loss=float(loss), d_radiance_abs_sum=float(d_rad.abs().sum()), d_params_abs_sum=(float(d_par_l1) if d_par_l1 is not None else None))
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

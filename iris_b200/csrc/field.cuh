@@ -245,17 +245,17 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P,
 #define FIELD_LD3 24   // leading dimension (halfs) of the 16-wide operands (dy^, W3^T)
 #define FIELD_BWD_WSM_HALFS ((64 + 64 + 16) * FIELD_LD + 2 * 64 * FIELD_LD + 64 * FIELD_LD3)
 #define FIELD_BWD_SMEM_BYTES (FIELD_BWD_WSM_HALFS * 2 + (IRIS_BLOCK / 32) * 32 * FIELD_LD * 2)
-#define FIELD_ACT_BYTES_PER_SAMPLE (5 * 128 + 32 + 4)   // X h1 h2 dh2^ dh1^ (64 halfs each) | dy^ (16 halfs) | s (float)
+#define FIELD_ACT_BYTES_PER_SAMPLE (6 * 128 + 32 + 4)   // X h1 h2 dh2^ dh1^ dx^ (64 halfs each) | dy^ (16 halfs) | s (float)
 
 struct FieldAct {   // SoA activation streams of one chunk of n samples
-    __half *X, *h1, *h2, *dh2, *dh1, *dy;
+    __half *X, *h1, *h2, *dh2, *dh1, *dx, *dy;
     float *s;
 };
 __host__ __device__ inline FieldAct field_act_carve(void *base, int64_t n) {
     FieldAct a;
     __half *p = reinterpret_cast<__half *>(base);
-    a.X = p; a.h1 = p + 64 * n; a.h2 = p + 128 * n; a.dh2 = p + 192 * n; a.dh1 = p + 256 * n; a.dy = p + 320 * n;
-    a.s = reinterpret_cast<float *>(p + 336 * n);
+    a.X = p; a.h1 = p + 64 * n; a.h2 = p + 128 * n; a.dh2 = p + 192 * n; a.dh1 = p + 256 * n; a.dx = p + 320 * n; a.dy = p + 384 * n;
+    a.s = reinterpret_cast<float *>(p + 400 * n);
     return a;
 }
 
@@ -319,9 +319,9 @@ __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
 
 // WS = true: positions/flags from the estimator record word r5 (x0.xyz, code), d_mat from the workspace; WS = false: plain arrays
 template <bool WS>
-__global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_dgrad(IrisShadeParams P, int64_t n, const float *__restrict__ position,
+__global__ void __launch_bounds__(IRIS_BLOCK, 4) k_field_backward_dgrad(IrisShadeParams P, int64_t n, const float *__restrict__ position,
                                                                       const float4 *__restrict__ r5, const float *__restrict__ d_mat,
-                                                                      FieldAct act, float *__restrict__ d_grid) {
+                                                                      FieldAct act) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half *Wsm = reinterpret_cast<__half *>(smem_raw);              // W1 | W2 | W3 (forward, [out][in])
     __half *W1T = Wsm + (64 + 64 + 16) * FIELD_LD;                     // [in][out] copies for dgrad
@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_dgrad(IrisShadePa
                     *reinterpret_cast<uint4 *>(act.h2 + (row0 + r) * 64 + c) = z;
                     *reinterpret_cast<uint4 *>(act.dh2 + (row0 + r) * 64 + c) = z;
                     *reinterpret_cast<uint4 *>(act.dh1 + (row0 + r) * 64 + c) = z;
+                    *reinterpret_cast<uint4 *>(act.dx + (row0 + r) * 64 + c) = z;
                 }
             }
             continue;
@@ -502,31 +503,95 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_dgrad(IrisShadePa
                 *reinterpret_cast<__half2 *>(r0 + 8 * FIELD_LD) = __floats2half2_rn(acc[mt][nt][2], acc[mt][nt][3]);
             }
         __syncwarp();
-        // ---- scatter s_i * w_corner * dx^ into the grid gradient (same indices / weights as the encoder)
-        if (active && sc > 0.f) {
-#pragma unroll 2
-            for (int l = 0; l < FIELD_LEVELS; ++l) {
-                const float2 dx = __half22float2(*reinterpret_cast<const __half2 *>(row + 2 * l));
-                const float gx = dx.x * sc, gy = dx.y * sc;
-                if (gx == 0.f && gy == 0.f) continue;
-                const FieldLevel L = c_levels[l];
-                const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
-                const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-                const float wx1 = xsub(px, fx), wy1 = xsub(py, fy), wz1 = xsub(pz, fz);
-                const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
-                const uint32_t cx = (uint32_t)__float2int_rz(fx), cy = (uint32_t)__float2int_rz(fy), cz = (uint32_t)__float2int_rz(fz);
+        warp_tile_to_global(Xs, act.dx, row0, n);      // dx^ (normalised): scattered into the grid by k_field_backward_scatter
+        __syncwarp();
+    }
+}
+
+// Kernel A2: one lane per sample, no gathers: recompute the encoder's indices / weights and add s_i * w_corner * dx^ to the grid
+// gradient with 8-byte vector reductions.  Consecutive lanes are the spp samples of one pixel, so on the coarse and middle
+// levels the whole warp (or a few groups of lanes) falls into the SAME grid cell: those lanes are reduced with shuffles first and
+// one lane per corner issues the reduction -- "reduce per warp, then one atomic per parameter tile" -- which removes the
+// same-address serialisation at the L2 atomic units.  Lanes in many different cells (fine levels) go straight to the reductions.
+#define FIELD_SCATTER_MAX_GROUPS 4
+template <bool WS>
+__global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams P, int64_t n, const float *__restrict__ position,
+                                                                 const float4 *__restrict__ r5, FieldAct act, float *__restrict__ d_grid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const float sc = i < n ? act.s[i] : 0.f;
+    const bool live = sc > 0.f;
+    if (!__any_sync(0xffffffffu, live)) return;
+    f3 p = mk3(0.f, 0.f, 0.f);
+    if (live) {
+        if (WS) { const float4 a = r5[i]; p = mk3(a.x, a.y, a.z); } else p = ld3(position, i);
+    }
+    const f3 x = mk3(field_coord(p.x, P.field_vmin, P.field_range), field_coord(p.y, P.field_vmin, P.field_range),
+                     field_coord(p.z, P.field_vmin, P.field_range));
+    const uint4 *row = reinterpret_cast<const uint4 *>(act.dx + 64 * (live ? i : 0));
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {              // 8 halfs = 4 levels per 16-byte load
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (live) v = __ldg(row + q);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int l = 4 * q + j;
+            const float2 dx = __half22float2(*reinterpret_cast<const __half2 *>(&w4[j]));
+            const float gx = dx.x * sc, gy = dx.y * sc;
+            const bool has = live && (gx != 0.f || gy != 0.f);
+            const FieldLevel L = c_levels[l];
+            const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
+            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+            const float wx1 = xsub(px, fx), wy1 = xsub(py, fy), wz1 = xsub(pz, fz);
+            const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
+            const uint32_t cx = (uint32_t)__float2int_rz(fx), cy = (uint32_t)__float2int_rz(fy), cz = (uint32_t)__float2int_rz(fz);
+            // exact cell key: coordinates of one level span < 2^17, so 21 bits per axis are injective
+            const unsigned long long key = has ? ((unsigned long long)(cx & 0x1FFFFFu) | ((unsigned long long)(cy & 0x1FFFFFu) << 21) |
+                                                  ((unsigned long long)(cz & 0x1FFFFFu) << 42))
+                                               : 0xFFFFFFFFFFFFFFFFull;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const bool leader = (unsigned)(__ffs(peers) - 1) == lane;
+            const unsigned leaders = __ballot_sync(0xffffffffu, leader && has);
+            float wc[8];
+            uint32_t idxc[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
-                    uint32_t idx;
-                    if (L.dense) idx = (ix + iy * L.res + iz * L.res * L.res) % L.size;
-                    else idx = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1u);
-                    const float w = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
-                    red_add_v2(d_grid + 2 * (int64_t)(L.offset + idx), w * gx, w * gy);
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
+                if (L.dense) idxc[c] = (ix + iy * L.res + iz * L.res * L.res) % L.size;
+                else idxc[c] = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1u);
+                wc[c] = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
+            }
+            if (__popc(leaders) <= FIELD_SCATTER_MAX_GROUPS) {
+                unsigned todo = leaders;
+                while (todo) {                                     // warp-uniform loop over the (few) distinct cells
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned long long k0 = __shfl_sync(0xffffffffu, key, src);
+                    const bool mine = has && key == k0;
+                    float sx[8], sy[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        sx[c] = mine ? wc[c] * gx : 0.f;
+                        sy[c] = mine ? wc[c] * gy : 0.f;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sx[c] += __shfl_xor_sync(0xffffffffu, sx[c], o);
+                            sy[c] += __shfl_xor_sync(0xffffffffu, sy[c], o);
+                        }
+                    }
+                    // lane src+c (mod 32) issues corner c: indices come from the group's leader
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t id = __shfl_sync(0xffffffffu, idxc[c], src);
+                        if (lane == (unsigned)c) red_add_v2(d_grid + 2 * (int64_t)(L.offset + id), sx[c], sy[c]);
+                    }
                 }
+            } else if (has) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) red_add_v2(d_grid + 2 * (int64_t)(L.offset + idxc[c]), wc[c] * gx, wc[c] * gy);
             }
         }
-        __syncwarp();
     }
 }
 
@@ -564,13 +629,46 @@ __device__ __forceinline__ void wgrad_tile(const __half *D, int ldd, const __hal
     }
 }
 
-#define FIELD_WGRAD_SMEM_BYTES (5 * 32 * FIELD_LD * 2 + 32 * FIELD_LD3 * 2 + 32 * 4)
+// Shared-memory image of one 32-sample tile: X | h1 | h2 | dh2^ | dh1^ (32 x 64 fp16, ld 72) | dy^ (32 x 16, ld 24) | s (32 floats)
+#define FIELD_WGRAD_TILE_BYTES (5 * 32 * FIELD_LD * 2 + 32 * FIELD_LD3 * 2 + 32 * 4)
+#define FIELD_WGRAD_STAGES 3
+#define FIELD_WGRAD_SMEM_BYTES (FIELD_WGRAD_STAGES * FIELD_WGRAD_TILE_BYTES)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;     // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+
+// issue the asynchronous copies of one tile (no registers staged, LDGSTS)
+__device__ __forceinline__ void wgrad_stage_tile(const FieldAct &act, int64_t row0, int64_t n, unsigned char *buf) {
+    __half *sX = reinterpret_cast<__half *>(buf);
+    for (int v = threadIdx.x; v < 5 * 256; v += IRIS_BLOCK) {
+        const int which = v >> 8, r = (v & 255) >> 3, c = (v & 7) * 8;
+        const __half *src = which == 0 ? act.X : which == 1 ? act.h1 : which == 2 ? act.h2 : which == 3 ? act.dh2 : act.dh1;
+        const bool ok = row0 + r < n;
+        cp_async16(sX + which * 32 * FIELD_LD + r * FIELD_LD + c, src + (ok ? (row0 + r) * 64 + c : 0), ok);
+    }
+    __half *sDy = sX + 5 * 32 * FIELD_LD;
+    float *sS = reinterpret_cast<float *>(sDy + 32 * FIELD_LD3);
+    if (threadIdx.x < 64) {
+        const int r = threadIdx.x >> 1, c = (threadIdx.x & 1) * 8;
+        const bool ok = row0 + r < n;
+        cp_async16(sDy + r * FIELD_LD3 + c, act.dy + (ok ? (row0 + r) * 16 + c : 0), ok);
+    } else if (threadIdx.x < 96) {
+        const int r = threadIdx.x - 64;
+        const bool ok = row0 + r < n;
+        cp_async4(sS + r, act.s + (ok ? row0 + r : 0), ok);
+    }
+}
+
 __global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_wgrad(FieldAct act, int64_t n, float *__restrict__ d_mlp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half *sX = reinterpret_cast<__half *>(smem_raw);
-    __half *sH1 = sX + 32 * FIELD_LD, *sH2 = sH1 + 32 * FIELD_LD, *sD2 = sH2 + 32 * FIELD_LD, *sD1 = sD2 + 32 * FIELD_LD;
-    __half *sDy = sD1 + 32 * FIELD_LD;
-    float *sS = reinterpret_cast<float *>(sDy + 32 * FIELD_LD3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     float a1[8][4], a2[8][4], a3[8][4];
 #pragma unroll
@@ -578,32 +676,35 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_wgrad(FieldAct ac
 #pragma unroll
         for (int k = 0; k < 4; ++k) a1[nt][k] = a2[nt][k] = a3[nt][k] = 0.f;
     const int64_t n_tiles = (n + 31) / 32;
+    // software pipeline: FIELD_WGRAD_STAGES tiles in flight per CTA
+    int64_t next = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < FIELD_WGRAD_STAGES - 1; ++s) {
+        if (next < n_tiles) wgrad_stage_tile(act, next * 32, n, smem_raw + s * FIELD_WGRAD_TILE_BYTES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        next += gridDim.x;
+    }
+    int stage = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * 32;
-        __syncthreads();
-        // stage the five 32x64 tiles (+ dy^, s) with coalesced 16-byte loads: 5 * 256 vectors over 128 threads
-        for (int v = threadIdx.x; v < 5 * 256; v += IRIS_BLOCK) {
-            const int which = v >> 8, r = (v & 255) >> 3, c = (v & 7) * 8;
-            const __half *src = which == 0 ? act.X : which == 1 ? act.h1 : which == 2 ? act.h2 : which == 3 ? act.dh2 : act.dh1;
-            __half *dst = which == 0 ? sX : which == 1 ? sH1 : which == 2 ? sH2 : which == 3 ? sD2 : sD1;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (row0 + r < n) val = *reinterpret_cast<const uint4 *>(src + (row0 + r) * 64 + c);
-            *reinterpret_cast<uint4 *>(dst + r * FIELD_LD + c) = val;
+        {   // prefetch tile + (STAGES-1) into the buffer freed by the previous iteration
+            const int ps = (stage + FIELD_WGRAD_STAGES - 1) % FIELD_WGRAD_STAGES;
+            if (next < n_tiles) wgrad_stage_tile(act, next * 32, n, smem_raw + ps * FIELD_WGRAD_TILE_BYTES);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            next += gridDim.x;
         }
-        if (threadIdx.x < 64) {
-            const int r = threadIdx.x >> 1, c = (threadIdx.x & 1) * 8;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (row0 + r < n) val = *reinterpret_cast<const uint4 *>(act.dy + (row0 + r) * 16 + c);
-            *reinterpret_cast<uint4 *>(sDy + r * FIELD_LD3 + c) = val;
-        } else if (threadIdx.x < 96) {
-            const int r = threadIdx.x - 64;
-            sS[r] = row0 + r < n ? act.s[row0 + r] : 0.f;
-        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(FIELD_WGRAD_STAGES - 1) : "memory");
         __syncthreads();
+        const __half *sX = reinterpret_cast<const __half *>(smem_raw + stage * FIELD_WGRAD_TILE_BYTES);
+        const __half *sH1 = sX + 32 * FIELD_LD, *sH2 = sH1 + 32 * FIELD_LD, *sD2 = sH2 + 32 * FIELD_LD, *sD1 = sD2 + 32 * FIELD_LD;
+        const __half *sDy = sD1 + 32 * FIELD_LD;
+        const float *sS = reinterpret_cast<const float *>(sDy + 32 * FIELD_LD3);
         wgrad_tile(sD1, FIELD_LD, sX, sS, 16 * warp, a1);     // dW1 rows [16w,16w+16)
         wgrad_tile(sD2, FIELD_LD, sH1, sS, 16 * warp, a2);    // dW2
         if (warp == 0) wgrad_tile(sDy, FIELD_LD3, sH2, sS, 0, a3);   // dW3 (16 rows)
+        __syncthreads();                                      // everyone is done with this buffer before it is refilled
+        stage = (stage + 1) % FIELD_WGRAD_STAGES;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // one atomic per weight per CTA
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {

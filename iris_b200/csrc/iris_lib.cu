@@ -39,8 +39,8 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
-enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_COUNT };
-static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish"};
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish"};
 struct ProfSpan { int id; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
@@ -282,6 +282,7 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_backward_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_WGRAD_SMEM_BYTES));
         attr_done = true;
     }
     const int64_t chunk = std::min<int64_t>(n, FIELD_BWD_CHUNK);
@@ -290,16 +291,23 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
         const int64_t m = std::min<int64_t>(chunk, n - c0);
         FieldAct act = field_act_carve(workspace, m);
         const int64_t tiles = (m + IRIS_BLOCK - 1) / IRIS_BLOCK;
-        const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 3);
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 4);
         {
             ProfScope ps(K_FIELD_BACKWARD, st);
-            if (r5) k_field_backward_dgrad<true><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act, d_params + 9216);
-            else k_field_backward_dgrad<false><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act, d_params + 9216);
+            if (r5) k_field_backward_dgrad<true><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act);
+            else k_field_backward_dgrad<false><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act);
+        }
+        LAUNCHED();
+        {
+            ProfScope ps(K_FIELD_SCATTER, st);
+            const unsigned gs = (unsigned)((m + 255) / 256);
+            if (r5) k_field_backward_scatter<true><<<gs, 256, 0, st>>>(*P, m, nullptr, r5 + c0, act, d_params + 9216);
+            else k_field_backward_scatter<false><<<gs, 256, 0, st>>>(*P, m, position + 3 * c0, nullptr, act, d_params + 9216);
         }
         LAUNCHED();
         {
             ProfScope ps(K_FIELD_WGRAD, st);
-            const unsigned g2 = (unsigned)std::min<int64_t>((m + 31) / 32, (int64_t)g_sm_count * 4);
+            const unsigned g2 = (unsigned)std::min<int64_t>((m + 31) / 32, (int64_t)g_sm_count * 3);
             k_field_backward_wgrad<<<g2, IRIS_BLOCK, FIELD_WGRAD_SMEM_BYTES, st>>>(act, m, d_params);
         }
         LAUNCHED();

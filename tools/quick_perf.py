@@ -57,6 +57,12 @@ def main():
     L, rec = core.single_forward(scene, tables, rays, spp, smp, True, ws)
     dL = torch.randn_like(L)
     ms = ev_time(lambda: core.single_backward(tables, dL, spp, rec), 3, 1); out["single_bwd_emitter_Msamples_s"] = rays.shape[0] * spp / ms / 1e3
+    dp = torch.zeros(9216 + 27954112, device=dev)
+    ws2 = torch.empty(core.C.lib().iris_single_workspace_bytes(rays.shape[0], spp), dtype=torch.uint8, device=dev)
+    ms = ev_time(lambda: core.single_backward(tables, dL, spp, rec, True, dp, ws2), 3, 1); out["single_bwd_brdf_Msamples_s"] = rays.shape[0] * spp / ms / 1e3
+    dm = torch.randn(x.shape[0], 5, device=dev) * 1e-4
+    wsf = torch.empty(core.C.lib().iris_field_backward_workspace_bytes(x.shape[0]), dtype=torch.uint8, device=dev)
+    ms = ev_time(lambda: core.field_backward(tables, x, dm, dp, wsf), 3, 1); out["field_bwd_Msamples_s"] = x.shape[0] / ms / 1e3
     out["L_mean"] = float(L.mean()); out["L_finite"] = bool(torch.isfinite(L).all())
     print(json.dumps(out, indent=1))
 
