@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P,
 // =====================================================================================================================
 #define FIELD_LD3 24   // leading dimension (halfs) of the 16-wide operands (dy^, W3^T)
 #define FIELD_BWD_WSM_HALFS ((64 + 64 + 16) * FIELD_LD + 2 * 64 * FIELD_LD + 64 * FIELD_LD3)
-#define FIELD_BWD_SMEM_BYTES (FIELD_BWD_WSM_HALFS * 2 + (IRIS_BLOCK / 32) * 32 * FIELD_LD * 2)
+#ifndef FIELD_BWD_BLOCK
+#define FIELD_BWD_BLOCK 256
+#endif
+#define FIELD_BWD_SMEM_BYTES (FIELD_BWD_WSM_HALFS * 2 + (FIELD_BWD_BLOCK / 32) * 32 * FIELD_LD * 2)
 #define FIELD_ACT_BYTES_PER_SAMPLE (6 * 128 + 32 + 4)   // X h1 h2 dh2^ dh1^ dx^ (64 halfs each) | dy^ (16 halfs) | s (float)
 
 struct FieldAct {   // SoA activation streams of one chunk of n samples
@@ -319,7 +322,7 @@ __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
 
 // WS = true: positions/flags from the estimator record word r5 (x0.xyz, code), d_mat from the workspace; WS = false: plain arrays
 template <bool WS>
-__global__ void __launch_bounds__(IRIS_BLOCK, 4) k_field_backward_dgrad(IrisShadeParams P, int64_t n, const float *__restrict__ position,
+__global__ void __launch_bounds__(FIELD_BWD_BLOCK, 512 / FIELD_BWD_BLOCK) k_field_backward_dgrad(IrisShadeParams P, int64_t n, const float *__restrict__ position,
                                                                       const float4 *__restrict__ r5, const float *__restrict__ d_mat,
                                                                       FieldAct act) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -342,9 +345,9 @@ __global__ void __launch_bounds__(IRIS_BLOCK, 4) k_field_backward_dgrad(IrisShad
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const __half2 *grid = reinterpret_cast<const __half2 *>(P.grid_f16);
-    const int64_t n_tiles = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
+    const int64_t n_tiles = (n + FIELD_BWD_BLOCK - 1) / FIELD_BWD_BLOCK;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * IRIS_BLOCK + (threadIdx.x & ~31);
+        const int64_t row0 = tile * FIELD_BWD_BLOCK + (threadIdx.x & ~31);
         const int64_t i = row0 + lane;
         bool active = i < n;
         f3 p = mk3(0.f, 0.f, 0.f);
@@ -513,7 +516,9 @@ __global__ void __launch_bounds__(IRIS_BLOCK, 4) k_field_backward_dgrad(IrisShad
 // levels the whole warp (or a few groups of lanes) falls into the SAME grid cell: those lanes are reduced with shuffles first and
 // one lane per corner issues the reduction -- "reduce per warp, then one atomic per parameter tile" -- which removes the
 // same-address serialisation at the L2 atomic units.  Lanes in many different cells (fine levels) go straight to the reductions.
+#ifndef FIELD_SCATTER_MAX_GROUPS
 #define FIELD_SCATTER_MAX_GROUPS 4
+#endif
 template <bool WS>
 __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams P, int64_t n, const float *__restrict__ position,
                                                                  const float4 *__restrict__ r5, FieldAct act, float *__restrict__ d_grid) {

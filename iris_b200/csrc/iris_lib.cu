@@ -290,12 +290,12 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t m = std::min<int64_t>(chunk, n - c0);
         FieldAct act = field_act_carve(workspace, m);
-        const int64_t tiles = (m + IRIS_BLOCK - 1) / IRIS_BLOCK;
-        const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 4);
+        const int64_t tiles = (m + FIELD_BWD_BLOCK - 1) / FIELD_BWD_BLOCK;
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * (512 / FIELD_BWD_BLOCK));
         {
             ProfScope ps(K_FIELD_BACKWARD, st);
-            if (r5) k_field_backward_dgrad<true><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act);
-            else k_field_backward_dgrad<false><<<grid, IRIS_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act);
+            if (r5) k_field_backward_dgrad<true><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act);
+            else k_field_backward_dgrad<false><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act);
         }
         LAUNCHED();
         {
