@@ -241,8 +241,9 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
     if (mode == 1) CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     const int64_t n = n_pixels * spp;
     ProfScope ps(mode == 0 ? K_BAKE_DIFFUSE : K_BAKE_SPECULAR, st);
-    if (mode == 0) k_bake<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
-    else k_bake<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
+    const unsigned gb = (unsigned)((n + IRIS_SORT_BLOCK - 1) / IRIS_SORT_BLOCK);
+    if (mode == 0) k_bake<0><<<gb, IRIS_SORT_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
+    else k_bake<1><<<gb, IRIS_SORT_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
     LAUNCHED();
     return IRIS_OK;
 }

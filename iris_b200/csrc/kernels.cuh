@@ -62,19 +62,20 @@ __device__ __forceinline__ f3 radiance_at_hit(const IrisShadeParams &P, const Hi
 // ------------------------------------------------------------------------------------------------ bake
 // bake_shading.py:108-123 (MODE 0) and :168-188 (MODE 1)
 template <int MODE>
-__global__ void __launch_bounds__(IRIS_BLOCK) k_bake(SceneView S, IrisShadeParams P, IrisSampler smp, float roughness,
-                                                      const float *__restrict__ position, const float *__restrict__ normal,
-                                                      const float *__restrict__ wo_in, int64_t n_pixels, int spp, float *out0, float *out1) {
+__global__ void __launch_bounds__(IRIS_SORT_BLOCK) k_bake(SceneView S, IrisShadeParams P, IrisSampler smp, float roughness,
+                                                           const float *__restrict__ position, const float *__restrict__ normal,
+                                                           const float *__restrict__ wo_in, int64_t n_pixels, int spp, float *out0, float *out1) {
+    __shared__ SortSmem sort;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = n_pixels * spp;
     const bool in_range = i < n;
     const int64_t pix = in_range ? i / spp : 0;
     f3 L0 = mk3(0.f, 0.f, 0.f), L1 = mk3(0.f, 0.f, 0.f);
+    f3 wi = mk3(0.f, 0.f, 1.f), org = mk3(0.f, 0.f, 0.f);
+    float w0 = 1.f, w1 = 0.f;
     if (in_range) {
         const f3 x = ld3(position, pix), nr = ld3(normal, pix);
         const float4 u = sample4(smp, i, 0);
-        f3 wi;
-        float w0 = 1.f, w1 = 0.f;
         if (MODE == 0) {
             wi = diffuse_sampler(u.x, u.y, nr);
         } else {
@@ -82,8 +83,10 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_bake(SceneView S, IrisShadeParam
             wi = specular_sampler(u.x, u.y, roughness, wo, nr);
             specular_weights(wi, wo, nr, roughness, w0, w1);
         }
-        const f3 org = mk3(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z);
-        const Hit h = trace_closest(S, org, wi);
+        org = mk3(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z);
+    }
+    const Hit h = block_sorted_trace<false>(S, sort, org, wi, in_range, __int_as_float(0x7f800000), -1);
+    if (in_range) {
         f3 hp, hn;
         hit_surface(S, h, wi, hp, hn);
         int32_t e;

@@ -9,6 +9,10 @@
 #include "bvh8.h"
 #include "common.cuh"
 
+#include <limits.h>
+#ifndef IRIS_SORT_BLOCK
+#define IRIS_SORT_BLOCK 256   // block size of the kernels that re-order their rays
+#endif
 #define IRIS_STACK 48   // one node group + one postponed triangle group per level: 2 * depth <= IRIS_STACK
 
 struct SceneView {
@@ -192,6 +196,82 @@ __device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
 __device__ __forceinline__ bool trace_occluded(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit) {
     return trace_ray<true>(S, o, d, t_limit, prim_limit).slot >= 0;
 }
+
+#ifndef IRIS_HOST_EMULATION
+// ------------------------------------------------------------------------------------------------------------------------
+// Block-cooperative ray re-ordering.  The lanes of a block hold the spp samples of a few neighbouring pixels: origins are
+// close together but directions cover the hemisphere, and a warp of such rays diverges after a couple of BVH levels (11-14
+// of 32 lanes active).  Before tracing, the block counting-sorts its rays by a 6-bit direction key (octant + which third of
+// the octant), each thread traces the ray that landed in ITS slot, and the hit goes back to the owner through shared memory.
+// Tracing is a pure function of the ray, so results are unchanged bit for bit; warps now hold rays inside a narrow cone.
+// Every thread of the block must call this (inactive lanes pass valid = false).
+// ------------------------------------------------------------------------------------------------------------------------
+struct SortSmem {
+    float ray[6][IRIS_SORT_BLOCK];      // o.xyz d.xyz of slot s
+    float lim[IRIS_SORT_BLOCK];         // t_limit
+    int plim[IRIS_SORT_BLOCK];          // prim_limit, or INT_MIN for an empty slot
+    float hit[3][IRIS_SORT_BLOCK];      // t u v
+    int hprim[IRIS_SORT_BLOCK], hslot[IRIS_SORT_BLOCK];
+    int hist[64], base[64];
+};
+
+__device__ __forceinline__ unsigned dir_key(f3 d) {
+    const unsigned oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const unsigned dom = ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u);          // dominant axis
+    const float m = fmaxf(ax, fmaxf(ay, az)), lo = dom == 0u ? fminf(ay, az) : dom == 1u ? fminf(ax, az) : fminf(ax, ay);
+    const unsigned steep = lo * 2.f > m ? 1u : 0u;                                          // near the octant diagonal or near the axis
+    return (oct << 3) | (dom << 1) | steep;
+}
+
+template <bool ANYHIT>
+__device__ __forceinline__ Hit block_sorted_trace(const SceneView &S, SortSmem &sm, f3 o, f3 d, bool valid, float t_limit, int32_t prim_limit) {
+    const int tid = threadIdx.x;
+    if (tid < 64) sm.hist[tid] = 0;
+    __syncthreads();
+    const unsigned key = dir_key(d);
+    int rank = 0;
+    if (valid) rank = atomicAdd(&sm.hist[key], 1);
+    sm.plim[tid] = INT_MIN;
+    __syncthreads();
+    if (tid < 32) {                                    // exclusive scan of the 64 bins by one warp
+        const int a = sm.hist[2 * tid], b = sm.hist[2 * tid + 1];
+        int s = a + b;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, s, o2);
+            if (tid >= o2) s += v;
+        }
+        sm.base[2 * tid] = s - a - b;
+        sm.base[2 * tid + 1] = s - b;
+    }
+    __syncthreads();
+    int slot = -1;
+    if (valid) {
+        slot = sm.base[key] + rank;
+        sm.ray[0][slot] = o.x; sm.ray[1][slot] = o.y; sm.ray[2][slot] = o.z;
+        sm.ray[3][slot] = d.x; sm.ray[4][slot] = d.y; sm.ray[5][slot] = d.z;
+        sm.lim[slot] = t_limit;
+        sm.plim[slot] = prim_limit;
+    }
+    __syncthreads();
+    if (sm.plim[tid] != INT_MIN) {
+        const f3 ro = mk3(sm.ray[0][tid], sm.ray[1][tid], sm.ray[2][tid]), rd = mk3(sm.ray[3][tid], sm.ray[4][tid], sm.ray[5][tid]);
+        const Hit h = trace_ray<ANYHIT>(S, ro, rd, sm.lim[tid], sm.plim[tid]);
+        sm.hit[0][tid] = h.t; sm.hit[1][tid] = h.u; sm.hit[2][tid] = h.v;
+        sm.hprim[tid] = h.prim; sm.hslot[tid] = h.slot;
+    }
+    __syncthreads();
+    Hit out;
+    out.t = t_limit; out.u = out.v = 0.f; out.prim = prim_limit; out.slot = -1;
+    if (valid) {
+        out.t = sm.hit[0][slot]; out.u = sm.hit[1][slot]; out.v = sm.hit[2][slot];
+        out.prim = sm.hprim[slot]; out.slot = sm.hslot[slot];
+    }
+    __syncthreads();                                   // the arrays are reused by the next call
+    return out;
+}
+#endif
 
 // Surface record of a hit: p = fma(v,e2,fma(u,e1,v0)), n = normalize(e1 x e2) flipped toward -d (oracle finish()).
 __device__ __forceinline__ void surface_from_triangle(const Hit &h, f3 d, f3 v0, f3 e1, f3 e2, f3 &p, f3 &n) {
