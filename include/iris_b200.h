@@ -181,6 +181,9 @@ int iris_trace_indirect(const IrisScene *scene, const IrisShadeParams *params, c
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t iris_launch_count(void);
 
+/* Implementation switches used for A/B measurements: "field_forward_impl" = 0 (mma.sync warp tiles) | 1 (tcgen05 + TMEM 128-row tiles). */
+int iris_set_option(const char *name, int value);
+
 /* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its own stream.
  * iris_profile_read synchronises the pending events and returns the launch count and the summed duration of one
  * kernel class (ids 0..13, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */

@@ -57,6 +57,7 @@ PROTOTYPES = {
                                              ctypes.POINTER(IrisSampler), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_trace_indirect": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(IrisSampler), c_vp, c_vp, c_i64, c_vp]),
     "iris_launch_count": (c_i64, []),
+    "iris_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "iris_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "iris_profile_name": (ctypes.c_char_p, [ctypes.c_int]),
     "iris_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_double), ctypes.c_int]),

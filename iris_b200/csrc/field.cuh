@@ -50,35 +50,127 @@ __device__ __forceinline__ float field_coord(float p, float vmin, float range) {
     return xsub(xmul(__fdiv_rn(xsub(p, vmin), range), 2.0f), 1.0f);
 }
 
-// Encodes one sample: writes 64 fp16 features to dst[0..63].
-__device__ __forceinline__ void field_encode(const __half2 *__restrict__ grid, f3 x, __half *dst) {
-#pragma unroll 2
-    for (int l = 0; l < FIELD_LEVELS; ++l) {
-        const FieldLevel L = c_levels[l];
-        const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
-        const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-        const float wx1 = xsub(px, fx), wy1 = xsub(py, fy), wz1 = xsub(pz, fz);
-        const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
-        const uint32_t cx = (uint32_t)__float2int_rz(fx), cy = (uint32_t)__float2int_rz(fy), cz = (uint32_t)__float2int_rz(fz);
-        __half2 v[8];
+// The first FIELD_DENSE_LEVELS levels are dense (x + y*res + z*res^2, modulo the level size because the reference feeds
+// negative coordinates that wrap in uint32); their res / size are compile-time constants of the fixed tcnn configuration, so the
+// modulo is a multiply-shift and the loop bodies are branch-free (the gathers of several levels can then be batched).
+#define FIELD_DENSE_LEVELS 7
+__device__ __host__ constexpr uint32_t field_dense_res(int l) { return l == 0 ? 16u : l == 1 ? 21u : l == 2 ? 28u : l == 3 ? 36u : l == 4 ? 46u : l == 5 ? 60u : 78u; }
+__device__ __host__ constexpr uint32_t field_dense_size(int l) { return (field_dense_res(l) * field_dense_res(l) * field_dense_res(l) + 7u) / 8u * 8u; }
+
+template <int DENSE_L>   // DENSE_L >= 0: dense level with compile-time geometry; -1: hashed level (size == 2^19)
+__device__ __forceinline__ void field_level_indices(const FieldLevel &L, f3 x, uint32_t idx[8], float w[8]) {
+    const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx1 = xsub(px, fx), wy1 = xsub(py, fy), wz1 = xsub(pz, fz);
+    const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
+    const uint32_t cx = (uint32_t)__float2int_rz(fx), cy = (uint32_t)__float2int_rz(fy), cz = (uint32_t)__float2int_rz(fz);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
-            uint32_t idx;
-            if (L.dense) idx = (ix + iy * L.res + iz * L.res * L.res) % L.size;
-            else idx = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1u);   // size == 2^19
-            v[c] = __ldg(grid + L.offset + idx);
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
+        if (DENSE_L >= 0) {
+            constexpr uint32_t res = field_dense_res(DENSE_L >= 0 ? DENSE_L : 0), size = field_dense_size(DENSE_L >= 0 ? DENSE_L : 0);
+            idx[c] = (ix + iy * res + iz * (res * res)) % size;
+        } else {
+            idx[c] = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & ((1u << 19) - 1u);
         }
-        float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float w = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
-            const float2 q = __half22float2(v[c]);
-            f0 = xadd(f0, xmul(w, q.x));
-            f1 = xadd(f1, xmul(w, q.y));
-        }
-        *reinterpret_cast<__half2 *>(dst + 2 * l) = __floats2half2_rn(f0, f1);
+        w[c] = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
     }
+}
+
+// corner weights only (second pass of the grouped encoder: recomputed instead of kept live across the gathers)
+__device__ __forceinline__ void field_level_weights(const FieldLevel &L, f3 x, float w[8]) {
+    const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
+    const float wx1 = xsub(px, floorf(px)), wy1 = xsub(py, floorf(py)), wz1 = xsub(pz, floorf(pz));
+    const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
+}
+
+template <int DENSE_L>
+__device__ __forceinline__ void field_level_gather(const __half2 *__restrict__ grid, f3 x, int l, __half2 v[8]) {
+    const FieldLevel L = c_levels[l];
+    uint32_t idx[8];
+    float w[8];
+    field_level_indices<DENSE_L>(L, x, idx, w);
+    // volatile asm keeps the gathers of a whole group in program order ahead of their consumers (ptxas otherwise sinks every load
+    // next to its use to save registers, leaving one or two requests in flight per lane)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t r;
+        asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(r) : "l"(grid + L.offset + idx[c]));
+        v[c] = *reinterpret_cast<__half2 *>(&r);
+    }
+}
+
+// Scheduling fence for a group of gathers.  ptxas sinks every load next to its first use to save registers, which leaves one or
+// two requests in flight per lane in a latency-bound loop.  Making every gathered word depend on ALL words of the group (xor with
+// `(w0^w1^...) & zero`, where `zero` is a run-time 0 the compiler cannot fold) forces the whole group to be issued first.
+template <int N>
+__device__ __forceinline__ void field_pin_group(__half2 (*v)[8], uint32_t zero) {
+    uint32_t tok = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) tok ^= *reinterpret_cast<uint32_t *>(&v[k][c]);
+    tok &= zero;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint32_t *>(&v[k][c]) ^= tok;
+}
+
+template <class Put>
+__device__ __forceinline__ void field_level_reduce(f3 x, int l, const __half2 v[8], Put &put) {
+    float w[8];
+    field_level_weights(c_levels[l], x, w);
+    float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float2 q = __half22float2(v[c]);
+        f0 = xadd(f0, xmul(w[c], q.x));
+        f1 = xadd(f1, xmul(w[c], q.y));
+    }
+    put(l, __floats2half2_rn(f0, f1));
+}
+
+// Encodes one sample: hands the 32 fp16 feature pairs (level l -> features 2l, 2l+1) to `put(l, pair)`.
+// The gathers of a GROUP of levels (4 dense, or 5 hashed: 32-40 independent 4-byte loads) are issued before anything is consumed,
+// so each lane keeps dozens of L2 requests in flight -- the encoder is latency-bound, not bandwidth-bound.
+template <class Put>
+__device__ __forceinline__ void field_encode_to(const __half2 *__restrict__ grid, f3 x, Put put) {
+    const uint32_t zero = c_levels[0].dense - 1u;      // 0 at run time (level 0 is dense), opaque to the compiler
+    {
+        __half2 v[4][8];
+        field_level_gather<0>(grid, x, 0, v[0]);
+        field_level_gather<1>(grid, x, 1, v[1]);
+        field_level_gather<2>(grid, x, 2, v[2]);
+        field_level_gather<3>(grid, x, 3, v[3]);
+        field_pin_group<4>(v, zero);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) field_level_reduce(x, k, v[k], put);
+    }
+    {
+        __half2 v[3][8];
+        field_level_gather<4>(grid, x, 4, v[0]);
+        field_level_gather<5>(grid, x, 5, v[1]);
+        field_level_gather<6>(grid, x, 6, v[2]);
+        field_pin_group<3>(v, zero);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) field_level_reduce(x, 4 + k, v[k], put);
+    }
+#pragma unroll 1
+    for (int l0 = FIELD_DENSE_LEVELS; l0 < FIELD_LEVELS; l0 += 5) {
+        __half2 v[5][8];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) field_level_gather<-1>(grid, x, l0 + k, v[k]);
+        field_pin_group<5>(v, zero);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) field_level_reduce(x, l0 + k, v[k], put);
+    }
+}
+// ... to a contiguous row dst[0..63]
+__device__ __forceinline__ void field_encode(const __half2 *__restrict__ grid, f3 x, __half *dst) {
+    field_encode_to(grid, x, [dst](int l, __half2 v) { *reinterpret_cast<__half2 *>(dst + 2 * l) = v; });
 }
 
 __device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], const uint32_t b[2]) {
@@ -547,10 +639,7 @@ __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams 
             const bool has = live && (gx != 0.f || gy != 0.f);
             const FieldLevel L = c_levels[l];
             const float px = __fmaf_rn(L.scale, x.x, 0.5f), py = __fmaf_rn(L.scale, x.y, 0.5f), pz = __fmaf_rn(L.scale, x.z, 0.5f);
-            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-            const float wx1 = xsub(px, fx), wy1 = xsub(py, fy), wz1 = xsub(pz, fz);
-            const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
-            const uint32_t cx = (uint32_t)__float2int_rz(fx), cy = (uint32_t)__float2int_rz(fy), cz = (uint32_t)__float2int_rz(fz);
+            const uint32_t cx = (uint32_t)__float2int_rz(floorf(px)), cy = (uint32_t)__float2int_rz(floorf(py)), cz = (uint32_t)__float2int_rz(floorf(pz));
             // exact cell key: coordinates of one level span < 2^17, so 21 bits per axis are injective
             const unsigned long long key = has ? ((unsigned long long)(cx & 0x1FFFFFu) | ((unsigned long long)(cy & 0x1FFFFFu) << 21) |
                                                   ((unsigned long long)(cz & 0x1FFFFFu) << 42))
@@ -560,12 +649,17 @@ __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams 
             const unsigned leaders = __ballot_sync(0xffffffffu, leader && has);
             float wc[8];
             uint32_t idxc[8];
+            if (l < FIELD_DENSE_LEVELS) {      // generic (runtime) dense indexing: 7 of 32 levels
+                const float wx1 = xsub(px, floorf(px)), wy1 = xsub(py, floorf(py)), wz1 = xsub(pz, floorf(pz));
+                const float wx0 = xsub(1.0f, wx1), wy0 = xsub(1.0f, wy1), wz0 = xsub(1.0f, wz1);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
-                if (L.dense) idxc[c] = (ix + iy * L.res + iz * L.res * L.res) % L.size;
-                else idxc[c] = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1u);
-                wc[c] = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
+                    idxc[c] = (ix + iy * L.res + iz * L.res * L.res) % L.size;
+                    wc[c] = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
+                }
+            } else {
+                field_level_indices<-1>(L, x, idxc, wc);
             }
             if (__popc(leaders) <= FIELD_SCATTER_MAX_GROUPS) {
                 unsigned todo = leaders;

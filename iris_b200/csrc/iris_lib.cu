@@ -9,6 +9,7 @@
 #include "../../include/iris_b200.h"
 #include "bvh8.h"
 #include "field.cuh"
+#include "field_tc5.cuh"
 #include "kernels.cuh"
 #include "wavefront.cuh"
 
@@ -69,12 +70,20 @@ static inline SceneView view_of(const IrisScene *s) {
 }
 
 static int g_sm_count = 0;
+static int g_tc5_ctas = 4;      // tcgen05 kernel: CTAs per SM (34.9 KB smem, 64 TMEM columns each)
+static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
 static bool g_field_ready[64] = {false};
 static int ensure_device_setup(int device) {
     if (device < 0 || device >= 64) return fail(IRIS_ERR_INVALID, "device index out of range");
     if (g_field_ready[device]) return IRIS_OK;
     FieldLevel lv[FIELD_LEVELS];
     field_level_table(lv);
+    for (int l = 0; l < FIELD_LEVELS; ++l) {      // the kernels hard-code the geometry of the dense levels and 2^19 for the hashed ones
+        const bool dense = l < FIELD_DENSE_LEVELS;
+        if ((lv[l].dense != 0) != dense || (dense && (lv[l].res != field_dense_res(l) || lv[l].size != field_dense_size(l))) ||
+            (!dense && lv[l].size != (1u << 19)))
+            return fail(IRIS_ERR_INVALID, "hash-grid level table does not match the compiled-in configuration");
+    }
     CUDA_TRY(cudaMemcpyToSymbol(c_levels, lv, sizeof(lv)));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -89,6 +98,21 @@ extern "C" {
 const char *iris_last_error(void) { return g_err.c_str(); }
 const char *iris_version(void) { return "iris_b200 0.1 sm_100a"; }
 int64_t iris_launch_count(void) { return g_launches.load(); }
+
+int iris_set_option(const char *name, int value) {
+    if (name && std::strcmp(name, "field_forward_impl") == 0 && (value == 0 || value == 1)) { g_field_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "tc5_ctas_per_sm") == 0 && value >= 1 && value <= 8) { g_tc5_ctas = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "field_smem_carveout_pct") == 0 && value >= 0 && value <= 100) {
+        // how much of the SM's 228 KB the field kernels ask to be shared memory: the rest is L1, which the hash-grid gathers live on
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward_tc5<true>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward_tc5<false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward<false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        return IRIS_OK;
+    }
+    if (name && std::strcmp(name, "tc5_debug") == 0) { CUDA_TRY(cudaMemcpyToSymbol(g_tc5_debug, &value, sizeof(int))); return IRIS_OK; }
+    return fail(IRIS_ERR_INVALID, "unknown option or value");
+}
 
 int iris_profile_enable(int on) {
     g_prof_on = on != 0;
@@ -253,13 +277,28 @@ static int launch_field(const IrisShadeParams *P, int64_t n, const float *positi
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_field_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC5_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC5_SMEM_BYTES));
+        // The encoder lives on L1: with the driver's default carveout for the tcgen05 kernel (all shared memory, no L1) it runs 2.4x
+        // slower.  70% of the SM's 228 KB as shared memory holds 4 CTAs and leaves ~68 KB of L1 for the hash-grid gathers
+        // (measured: 2.96 G samples/s on camera-coherent positions, 1.33 G/s on uniformly random ones; 35% favours the latter).
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward_tc5<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+        CUDA_TRY(cudaFuncSetAttribute(k_field_forward_tc5<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
         attr_done = true;
     }
     const int64_t tiles = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * 4);
     ProfScope ps(K_FIELD_FORWARD, st);
-    if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
-    else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+    if (g_field_impl == 1) {
+        const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * g_tc5_ctas);
+        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+    } else {
+        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+    }
     LAUNCHED();
     return IRIS_OK;
 }

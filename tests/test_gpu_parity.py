@@ -476,3 +476,18 @@ def test_path_tracing_parity_is_tight_for_a_smooth_field(small):
     got = core.path_tracing(small["scene"], tables, r.to(dev), spp, depth, core.Sampler(U=U.to(dev)))
     frac, worst = _frac_close(got.cpu().numpy(), ref.numpy())
     assert frac >= 0.99 and worst < 1e-2, (frac, worst)
+
+
+def test_tcgen05_field_kernel_equals_mma_sync_kernel(small):
+    """The default BRDF-field forward runs on tcgen05 tensor cores with TMEM accumulators (k_field_forward_tc5); the warp-level
+    mma.sync kernel it replaced is kept behind a measurement switch.  Same rounding points -> identical outputs."""
+    from iris_b200 import core
+    lib = core.C.lib()
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 127, 128, 129, 70001):
+        x = (torch.rand(n, 3, generator=g) * 2.2 - 1.1).to(small["dev"])
+        core.C.check(lib.iris_set_option(b"field_forward_impl", 0))
+        a = core.field_forward(small["tables"], x)
+        core.C.check(lib.iris_set_option(b"field_forward_impl", 1))
+        b = core.field_forward(small["tables"], x)
+        assert torch.equal(a, b), n

@@ -22,3 +22,11 @@ ms = ev_time(lambda: core.field_backward(tables, x, dm, dp, ws), 3, 1)
 print(json.dumps({"n": x.shape[0], "field_bwd_coherent_Msamples_s": x.shape[0] / ms / 1e3}))
 ms = ev_time(lambda: core.field_forward(tables, x), 3, 1)
 print(json.dumps({"field_fwd_coherent_Msamples_s": x.shape[0] / ms / 1e3}))
+lib = core.C.lib()
+for impl in (0, 1):
+    for ctas in (2, 4, 6):
+        for pct in (35, 50, 70):
+            lib.iris_set_option(b"field_forward_impl", impl); lib.iris_set_option(b"tc5_ctas_per_sm", ctas); lib.iris_set_option(b"field_smem_carveout_pct", pct)
+            ms = ev_time(lambda: core.field_forward(tables, x), 3, 1)
+            print("impl", impl, "ctas", ctas, "carveout", pct, "coherent fwd Msamples/s %.0f" % (x.shape[0] / ms / 1e3))
+        if impl == 0: break
