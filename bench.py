@@ -37,6 +37,10 @@ WORKLOADS = {
                desc="training step: path_tracing_single fwd+bwd with gradients to the BRDF field (hash grid + MLP) AND emitter radiance, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), random-init field, K=16, MIS on"),
     "c4": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32, brdf_grad=False,
                desc="train_emitter step: path_tracing_single fwd+bwd, emitter-radiance gradient, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), K=16, MIS on"),
+    "c5": dict(tris=5_000_000, emitters=16, views=64, width=1920, height=1440, SPP=128, spp=128, brdf_grad=True, strong=True,
+               desc="scaling sweep: 5M-tri room, 64 views 1920x1440 in total (sharded over the GPUs), spp=128, path_tracing_single fwd+bwd, field + emitter gradients"),
+    "c2": dict(tris=1_000_000, emitters=16, views=1, width=640, height=480, SPP=64, spp=64, brdf_grad=False, bake=True,
+               desc="shading-map bake (bake_shading.py): 1M-tri room, 640x480, spp=64, diffuse map + 6 roughness levels x 2 Fresnel maps, forward only"),
     "c1": dict(tris=10_000, emitters=2, views=1, width=64, height=64, SPP=16, spp=16, brdf_grad=True,
                desc="Cornell ~10k tris, 64x64, spp=16, path_tracing_single fwd+bwd (reference's CPU-runnable case)"),
 }
@@ -159,6 +163,55 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
+# ------------------------------------------------------------------------------------------------ bake (configs[1], forward only)
+def bench_bake(a, w, sc, scene, tables, dev, config, stats):
+    """One step = the bake of one 640x480 training view: primary hits (ray_intersect), then per pixel spp secondary rays for the
+    diffuse map and for each of the 6 roughness levels (two Fresnel maps each) -- 7 fused launches (bake_shading.py:93-204)."""
+    import torch
+    from iris_b200 import core
+    lib = core.C.lib()
+    rays = torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=1)).to(dev)
+    spp = w["spp"]
+    levels = [0.02 + 0.98 * i / 5 for i in range(6)]
+
+    def step(s):
+        t, prim, uv, p, n = scene.intersect_raw(rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous())
+        valid = prim >= 0
+        pos, nrm, wo = p[valid].contiguous(), n[valid].contiguous(), (-rays[:, 3:6])[valid].contiguous()
+        outs = [core.bake(scene, tables, 0, 1.0, pos, nrm, None, spp, core.Sampler(seed=10 + s))]
+        for i, r in enumerate(levels):
+            outs += list(core.bake(scene, tables, 1, r, pos, nrm, wo, spp, core.Sampler(seed=100 * (i + 1) + s)))
+        return pos.shape[0], outs
+
+    for s in range(max(a.warmup, 3)):
+        npx, _ = step(s)
+    torch.cuda.synchronize()
+    l0 = lib.iris_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(a.steps):
+        npx, outs = step(100 + s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n_rays = (npx * spp * 7 + rays.shape[0]) * a.steps
+    peak = 6518.6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    bpr = ray_bytes(sc.n_tris) + 16 + 36.0 / spp
+    value = n_rays / (ms * 1e-3)
+    line = dict(metric="shading_map_bake_rays_per_sec", value=value, unit="rays/s", n_gpus=1, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms / a.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                gpu_launches=int(lib.iris_launch_count() - l0),
+                roofline=dict(bound="hbm", kernel="k_bake", achieved=value * bpr / 1e9, peak=peak, unit="GB/s", frac=value * bpr / 1e9 / peak, traffic=None,
+                              algorithmic_bytes_per_ray=bpr),
+                scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
+                maps_finite=bool(all(torch.isfinite(o).all() for o in outs)))
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     a = parse()
@@ -206,7 +259,13 @@ def main():
     scene = core.Scene(sc.vertices, sc.faces, local)
     stats = scene.stats()
     tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(256), bench_params(), sc.voxel_bounds())
-    views = [rank * w["views"] + v + 1 for v in range(w["views"])]
+    if w.get("bake"):
+        return bench_bake(a, w, sc, scene, tables, dev, config, stats)
+    if w.get("strong"):                                   # fixed total work, views sharded over the ranks
+        lo_v, hi_v = idist.shard_range(w["views"], rank, world)
+        views = [v + 1 for v in range(lo_v, hi_v)]
+    else:
+        views = [rank * w["views"] + v + 1 for v in range(w["views"])]
     rays_host = torch.cat([torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=v)) for v in views]).pin_memory()
     rays_dev = rays_host.to(dev)
     P = rays_host.shape[0]
@@ -343,7 +402,7 @@ def main():
         cb, _ = cpu_leg(w, sc, a.cpu_sample_pixels, 1, 1)
 
     line = dict(metric="path_samples_per_sec_fwd_bwd", value=value, unit="samples/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-                ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                ms_per_step=ms / a.steps, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cb,
                 scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
                 loss=float(loss), d_radiance_abs_sum=float(d_rad.abs().sum()), d_params_abs_sum=(float(d_par_l1) if d_par_l1 is not None else None))

@@ -44,7 +44,8 @@ const char *iris_version(void);
  * Scene: one triangle mesh + 8-wide compressed BVH resident in HBM.
  * Replaces mitsuba.load_dict({'type':'scene','shape_id':{'type':'obj'|'ply',...}})
  * (train_emitter.py:57-63, bake_shading.py:55-61); prim index = face order of `faces`.
- * verts/faces are HOST pointers.  builder: 0 = host binned-SAH (default), 1 = on-device LBVH.
+ * verts/faces are HOST pointers.  builder: 1 = on-device Morton LBVH -> 8-wide collapse (15 ms per 1M triangles; what the Python layer
+ * uses), 0 = host binned-SAH (0.7 s per 1M triangles).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct IrisScene IrisScene;
 

@@ -28,6 +28,8 @@ struct Node2 {
     Box box;
     int32_t left;   // inner: index of left child (right = left + 1); leaf: first primitive
     int32_t count;  // 0 = inner
+    int32_t first;  // first primitive of the subtree (primitives of a subtree are contiguous in `order`)
+    int32_t total;  // primitives in the subtree
 };
 
 constexpr int kBins = 16;
@@ -55,6 +57,8 @@ struct Builder {
                 cb.grow(&cent[3 * (size_t)order[i]]);
             }
             nodes[j.node].box = b;
+            nodes[j.node].first = j.first;
+            nodes[j.node].total = j.count;
             if (j.count == 1) { nodes[j.node].left = j.first; nodes[j.node].count = j.count; continue; }
             // binned SAH over the three axes
             float best_cost = INFINITY;
@@ -176,7 +180,7 @@ int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, in
     B.nodes.reserve((size_t)(2 * F + 2));
     B.nodes.push_back(Node2());
     if (F > 0) B.build_range(0, 0, (int32_t)F);
-    else { B.nodes[0].box = scene; B.nodes[0].left = 0; B.nodes[0].count = 0; }
+    else { B.nodes[0].box = scene; B.nodes[0].left = 0; B.nodes[0].count = 0; B.nodes[0].first = 0; B.nodes[0].total = 0; }
 
     // ---- collapse to 8-wide, breadth-first so that the children of a node are contiguous
     std::vector<Bvh8Node> wide;
@@ -197,8 +201,8 @@ int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, in
         int nch = 0;
         if (F == 0) {
             nch = 0;
-        } else if (B.nodes[n2].count > 0) {
-            ch[nch++] = n2;   // degenerate root leaf
+        } else if (B.nodes[n2].total <= kMaxLeaf) {
+            ch[nch++] = n2;   // tiny scene: the root itself is a leaf child
         } else {
             ch[nch++] = B.nodes[n2].left;
             ch[nch++] = B.nodes[n2].left + 1;
@@ -206,7 +210,7 @@ int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, in
                 int best = -1;
                 float ba = -1.f;
                 for (int i = 0; i < nch; ++i)
-                    if (B.nodes[ch[i]].count == 0) {
+                    if (B.nodes[ch[i]].total > kMaxLeaf) {      // a subtree of <= 3 triangles is ONE leaf child, whatever its shape
                         float a = B.nodes[ch[i]].box.area();
                         if (a > ba) { ba = a; best = i; }
                     }
@@ -276,7 +280,7 @@ int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, in
                 qlo[k][s] = (uint8_t)std::max(0.0, std::min(255.0, lo));
                 qhi[k][s] = (uint8_t)std::max(0.0, std::min(255.0, hi));
             }
-            if (c.count == 0) {
+            if (c.total > kMaxLeaf) {
                 N.imask |= (uint8_t)(1u << s);
                 N.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 wide.push_back(Bvh8Node());
@@ -284,10 +288,10 @@ int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, in
                 depth.push_back(depth[wi] + 1);
                 max_depth = std::max(max_depth, depth[wi] + 1);
             } else {
-                const uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
+                const uint32_t unary = c.total == 1 ? 1u : (c.total == 2 ? 3u : 7u);
                 N.meta[s] = (uint8_t)((unary << 5) | tri_off);
-                for (int32_t t = 0; t < c.count; ++t) tris.push_back(recs[(size_t)B.order[(size_t)(c.left + t)]]);
-                tri_off += (uint32_t)c.count;
+                for (int32_t t = 0; t < c.total; ++t) tris.push_back(recs[(size_t)B.order[(size_t)(c.first + t)]]);
+                tri_off += (uint32_t)c.total;
             }
         }
         wide[wi] = N;

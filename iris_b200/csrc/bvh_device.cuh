@@ -1,0 +1,290 @@
+// bvh_device.cuh -- on-device builder (builder = 1): Morton-ordered LBVH (Karras 2012) -> greedy collapse to 8-wide ->
+// octant slot assignment -> conservative 8-bit quantisation, producing exactly the node / triangle layout of bvh8.h.
+// Milliseconds instead of the host builder's ~0.7 s per million triangles; tree quality is LBVH (no SAH), so traversal is
+// somewhat slower -- the host binned-SAH builder stays the default for static scenes, this one is for scenes that change.
+// Hit results do not depend on the builder: traversal is exact (tests run both).
+#pragma once
+#include <cub/cub.cuh>
+
+#include "bvh8.h"
+#include "common.cuh"
+
+struct DBox {
+    float lo[3], hi[3];
+};
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {   // spread 21 bits to every third bit
+    v &= 0x1FFFFFull;
+    v = (v | v << 32) & 0x1F00000000FFFFull;
+    v = (v | v << 16) & 0x1F0000FF0000FFull;
+    v = (v | v << 8) & 0x100F00F00F00F00Full;
+    v = (v | v << 4) & 0x10C30C30C30C30C3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__device__ __forceinline__ void atomic_min_f(float *a, float v) {
+    int *ai = reinterpret_cast<int *>(a);
+    int old = *ai;
+    while (v < __int_as_float(old)) {
+        const int prev = atomicCAS(ai, old, __float_as_int(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+__device__ __forceinline__ void atomic_max_f(float *a, float v) {
+    int *ai = reinterpret_cast<int *>(a);
+    int old = *ai;
+    while (v > __int_as_float(old)) {
+        const int prev = atomicCAS(ai, old, __float_as_int(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+// records + unpadded boxes + scene bounds (bounds[0..2] = lo, [3..5] = hi)
+__global__ void k_lbvh_prepare(const float *__restrict__ verts, const int32_t *__restrict__ faces, int n, TriRecord *recs, DBox *tbox, float *bounds) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (f < n) {
+        const float *a = verts + 3 * (int64_t)faces[3 * f], *b = verts + 3 * (int64_t)faces[3 * f + 1], *c = verts + 3 * (int64_t)faces[3 * f + 2];
+        TriRecord r;
+        for (int k = 0; k < 3; ++k) {
+            r.v0[k] = a[k];
+            r.e1[k] = __fsub_rn(b[k], a[k]);
+            r.e2[k] = __fsub_rn(c[k], a[k]);
+            const float p1 = __fadd_rn(r.v0[k], r.e1[k]), p2 = __fadd_rn(r.v0[k], r.e2[k]);
+            lo[k] = fminf(fminf(a[k], fminf(b[k], c[k])), fminf(p1, p2));
+            hi[k] = fmaxf(fmaxf(a[k], fmaxf(b[k], c[k])), fmaxf(p1, p2));
+        }
+        const float cx = __fsub_rn(__fmul_rn(r.e1[1], r.e2[2]), __fmul_rn(r.e1[2], r.e2[1]));
+        const float cy = __fsub_rn(__fmul_rn(r.e1[2], r.e2[0]), __fmul_rn(r.e1[0], r.e2[2]));
+        const float cz = __fsub_rn(__fmul_rn(r.e1[0], r.e2[1]), __fmul_rn(r.e1[1], r.e2[0]));
+        if (cx == 0.f && cy == 0.f && cz == 0.f)
+            for (int k = 0; k < 3; ++k) r.e1[k] = r.e2[k] = 0.f;      // zero-area triangle: never hit (oracle rule)
+        r.prim = f;
+        r.pad[0] = r.pad[1] = 0;
+        recs[f] = r;
+        DBox bx;
+        for (int k = 0; k < 3; ++k) { bx.lo[k] = lo[k]; bx.hi[k] = hi[k]; }
+        tbox[f] = bx;
+    }
+    // block reduction of the bounds, one atomic per block and component
+    __shared__ float s[6][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 3; ++k) {
+        float a = lo[k], b = hi[k];
+        for (int o = 16; o > 0; o >>= 1) { a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+        if (lane == 0) { s[k][warp] = a; s[3 + k][warp] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s[threadIdx.x][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = threadIdx.x < 3 ? fminf(v, s[threadIdx.x][w]) : fmaxf(v, s[threadIdx.x][w]);
+        if (threadIdx.x < 3) atomic_min_f(bounds + threadIdx.x, v); else atomic_max_f(bounds + threadIdx.x, v);
+    }
+}
+
+__global__ void k_lbvh_morton(const DBox *__restrict__ tbox, int n, const float *__restrict__ bounds, unsigned long long *keys, uint32_t *idx) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    unsigned long long code = 0;
+    for (int k = 0; k < 3; ++k) {
+        const float c = 0.5f * (tbox[f].lo[k] + tbox[f].hi[k]);
+        const float ext = fmaxf(bounds[3 + k] - bounds[k], 1e-30f);
+        const float u = fminf(fmaxf((c - bounds[k]) / ext, 0.f), 1.f);
+        const unsigned long long q = (unsigned long long)fminf(u * 2097152.f, 2097151.f);
+        code |= expand21(q) << (2 - k);
+    }
+    keys[f] = code;
+    idx[f] = (uint32_t)f;
+}
+
+// Binary radix tree.  Nodes: internal i in [0,n-1), leaf k at n-1+k.
+struct LbvhNodes {
+    int2 *child;      // internal: (left, right) node ids
+    int *parent;      // all 2n-1 nodes
+    int2 *range;      // internal: [first,last] sorted leaf range
+    DBox *box;        // all 2n-1 nodes (padded)
+    int *flag;        // internal: arrival counter
+};
+
+__device__ __forceinline__ int lbvh_delta(const unsigned long long *__restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long x = keys[i] ^ keys[j];
+    return x == 0ull ? 64 + __clz(i ^ j) : __clzll((long long)x);
+}
+
+__global__ void k_lbvh_hierarchy(const unsigned long long *__restrict__ keys, int n, LbvhNodes N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const int left = first == gamma ? (n - 1 + gamma) : gamma;
+    const int right = last == gamma + 1 ? (n - 1 + gamma + 1) : gamma + 1;
+    N.child[i] = make_int2(left, right);
+    N.range[i] = make_int2(first, last);
+    N.parent[left] = i;
+    N.parent[right] = i;
+    if (i == 0) N.parent[0] = -1;
+}
+
+__global__ void k_lbvh_fit(const DBox *__restrict__ tbox, const uint32_t *__restrict__ sorted, int n, const float *__restrict__ bounds, LbvhNodes N) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float ext = 0.f, amax = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        ext = fmaxf(ext, bounds[3 + a] - bounds[a]);
+        amax = fmaxf(amax, fmaxf(fabsf(bounds[a]), fabsf(bounds[3 + a])));
+    }
+    const float pad = 1e-5f * fmaxf(ext, amax) + 1e-30f;      // same conservative padding as the host builder
+    DBox b = tbox[sorted[k]];
+    for (int a = 0; a < 3; ++a) { b.lo[a] -= pad; b.hi[a] += pad; }
+    int node = n - 1 + k;
+    N.box[node] = b;
+    if (n == 1) return;
+    int p = N.parent[node];
+    while (p >= 0) {
+        __threadfence();
+        if (atomicAdd(&N.flag[p], 1) == 0) return;            // first child to arrive leaves; the second one fits the parent
+        const int2 c = N.child[p];
+        const DBox x = N.box[c.x], y = N.box[c.y];
+        for (int a = 0; a < 3; ++a) { b.lo[a] = fminf(x.lo[a], y.lo[a]); b.hi[a] = fmaxf(x.hi[a], y.hi[a]); }
+        N.box[p] = b;
+        p = N.parent[p];
+    }
+}
+
+__device__ __forceinline__ float dbox_area(const DBox &b) {
+    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+__device__ __forceinline__ int lbvh_count(const LbvhNodes &N, int n, int node) {
+    if (node >= n - 1) return 1;
+    const int2 r = N.range[node];
+    return r.y - r.x + 1;
+}
+__device__ __forceinline__ int lbvh_first(const LbvhNodes &N, int n, int node) { return node >= n - 1 ? node - (n - 1) : N.range[node].x; }
+
+__device__ __forceinline__ uint8_t dev_exp_for_extent(double ext) {
+    if (!(ext > 0.0)) return (uint8_t)1;
+    int e = (int)ceil(log2(ext / 255.0));
+    while (ldexp(255.0, e) < ext) ++e;
+    e = max(-126, min(127, e));
+    return (uint8_t)(e + 127);
+}
+
+// One thread per wide node of the current level [begin,end): wide_bin[w] = binary node it represents.
+__global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const TriRecord *__restrict__ recs, const uint32_t *__restrict__ sorted,
+                                int *wide_bin, int *wide_depth, Bvh8Node *wide, TriRecord *tris_out, int *counters /* [0]=nodes [1]=tris [2]=max depth */) {
+    const int w = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    const int bnode = wide_bin[w];
+    int ch[8];
+    int nch = 0;
+    if (lbvh_count(N, n, bnode) <= 3) {
+        ch[nch++] = bnode;                                   // tiny scene: the root itself is a leaf child
+    } else {
+        const int2 c = N.child[bnode];
+        ch[nch++] = c.x;
+        ch[nch++] = c.y;
+        while (nch < 8) {
+            int best = -1;
+            float ba = -1.f;
+            for (int i = 0; i < nch; ++i)
+                if (lbvh_count(N, n, ch[i]) > 3) {
+                    const float a = dbox_area(N.box[ch[i]]);
+                    if (a > ba) { ba = a; best = i; }
+                }
+            if (best < 0) break;
+            const int2 c2 = N.child[ch[best]];
+            ch[best] = c2.x;
+            ch[nch++] = c2.y;
+        }
+    }
+    DBox nb;
+    for (int a = 0; a < 3; ++a) { nb.lo[a] = INFINITY; nb.hi[a] = -INFINITY; }
+    for (int i = 0; i < nch; ++i) {
+        const DBox b = N.box[ch[i]];
+        for (int a = 0; a < 3; ++a) { nb.lo[a] = fminf(nb.lo[a], b.lo[a]); nb.hi[a] = fmaxf(nb.hi[a], b.hi[a]); }
+    }
+    // slot assignment: greedy minimum of dot(centroid_child - centroid_node, D_slot)
+    int child_in_slot[8], slot_of[8];
+    for (int s = 0; s < 8; ++s) { child_in_slot[s] = -1; slot_of[s] = -1; }
+    float cost[8][8];
+    for (int i = 0; i < nch; ++i) {
+        const DBox b = N.box[ch[i]];
+        float cc[3];
+        for (int a = 0; a < 3; ++a) cc[a] = 0.5f * (b.lo[a] + b.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+        for (int s = 0; s < 8; ++s) cost[i][s] = cc[0] * ((s & 4) ? -1.f : 1.f) + cc[1] * ((s & 2) ? -1.f : 1.f) + cc[2] * ((s & 1) ? -1.f : 1.f);
+    }
+    for (int it = 0; it < nch; ++it) {
+        float bc = INFINITY;
+        int bi = -1, bs = -1;
+        for (int i = 0; i < nch; ++i) {
+            if (slot_of[i] >= 0) continue;
+            for (int s = 0; s < 8; ++s)
+                if (child_in_slot[s] < 0 && cost[i][s] < bc) { bc = cost[i][s]; bi = i; bs = s; }
+        }
+        slot_of[bi] = bs;
+        child_in_slot[bs] = bi;
+    }
+    int n_inner = 0, n_tris = 0;
+    for (int i = 0; i < nch; ++i) {
+        const int c = lbvh_count(N, n, ch[i]);
+        if (c > 3) ++n_inner; else n_tris += c;
+    }
+    const int child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0;
+    const int tri_base = n_tris ? atomicAdd(&counters[1], n_tris) : 0;
+    const int depth = wide_depth[w];
+    if (n_inner) atomicMax(&counters[2], depth + 1);
+    Bvh8Node O;
+    memset(&O, 0, sizeof(O));
+    for (int a = 0; a < 3; ++a) {
+        O.p[a] = nb.lo[a];
+        O.e[a] = dev_exp_for_extent((double)nb.hi[a] - (double)nb.lo[a]);
+    }
+    O.child_base = (uint32_t)child_base;
+    O.tri_base = (uint32_t)tri_base;
+    int inner_i = 0, tri_off = 0;
+    for (int s = 0; s < 8; ++s) {
+        const int i = child_in_slot[s];
+        if (i < 0) continue;
+        const DBox b = N.box[ch[i]];
+        uint8_t *qlo[3] = {O.qlo_x, O.qlo_y, O.qlo_z}, *qhi[3] = {O.qhi_x, O.qhi_y, O.qhi_z};
+        for (int a = 0; a < 3; ++a) {
+            const double sc = ldexp(1.0, (int)O.e[a] - 127);
+            qlo[a][s] = (uint8_t)fmax(0.0, fmin(255.0, floor(((double)b.lo[a] - (double)O.p[a]) / sc)));
+            qhi[a][s] = (uint8_t)fmax(0.0, fmin(255.0, ceil(((double)b.hi[a] - (double)O.p[a]) / sc)));
+        }
+        const int c = lbvh_count(N, n, ch[i]);
+        if (c > 3) {
+            O.imask |= (uint8_t)(1u << s);
+            O.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            wide_bin[child_base + inner_i] = ch[i];
+            wide_depth[child_base + inner_i] = depth + 1;
+            ++inner_i;
+        } else {
+            const uint32_t unary = c == 1 ? 1u : (c == 2 ? 3u : 7u);
+            O.meta[s] = (uint8_t)((unary << 5) | (uint32_t)tri_off);
+            const int first = lbvh_first(N, n, ch[i]);
+            for (int t = 0; t < c; ++t) tris_out[tri_base + tri_off + t] = recs[sorted[first + t]];
+            tri_off += c;
+        }
+    }
+    wide[w] = O;
+}

@@ -8,6 +8,7 @@
 
 #include "../../include/iris_b200.h"
 #include "bvh8.h"
+#include "bvh_device.cuh"
 #include "field.cuh"
 #include "field_tc5.cuh"
 #include "kernels.cuh"
@@ -93,6 +94,95 @@ static int ensure_device_setup(int device) {
     return IRIS_OK;
 }
 
+// ---- builder = 1: everything on the device (bvh_device.cuh)
+#define CUDA_OK(x)                                              \
+    do {                                                        \
+        e = (x);                                                \
+        if (e != cudaSuccess) goto done;                        \
+    } while (0)
+static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces, IrisScene *s) {
+    cudaError_t e = cudaSuccess;
+    const int n = (int)n_faces;
+    float *d_verts = nullptr, *d_bounds = nullptr;
+    int32_t *d_faces = nullptr;
+    TriRecord *d_recs = nullptr, *d_tris = nullptr;
+    DBox *d_tbox = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    uint32_t *d_idx = nullptr, *d_idx2 = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    LbvhNodes N{};
+    int *d_wide_bin = nullptr, *d_wide_depth = nullptr, *d_counters = nullptr;
+    Bvh8Node *d_wide = nullptr;
+    int counters[3] = {1, 0, 1};
+    const float binit[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float hb[6];
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    CUDA_OK(cudaMalloc(&d_verts, sizeof(float) * 3 * (size_t)std::max<int64_t>(n_verts, 1)));
+    CUDA_OK(cudaMalloc(&d_faces, sizeof(int32_t) * 3 * (size_t)n));
+    CUDA_OK(cudaMemcpy(d_verts, verts, sizeof(float) * 3 * (size_t)n_verts, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_faces, faces, sizeof(int32_t) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&d_recs, sizeof(TriRecord) * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_tris, sizeof(TriRecord) * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_tbox, sizeof(DBox) * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_bounds, sizeof(float) * 6));
+    CUDA_OK(cudaMemcpy(d_bounds, binit, sizeof(binit), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&d_keys, 8 * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_keys2, 8 * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_idx, 4 * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_idx2, 4 * (size_t)n));
+    k_lbvh_prepare<<<gb, 256>>>(d_verts, d_faces, n, d_recs, d_tbox, d_bounds);
+    k_lbvh_morton<<<gb, 256>>>(d_tbox, n, d_bounds, d_keys, d_idx);
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, n, 0, 63));
+    CUDA_OK(cudaMalloc(&d_tmp, tmp_bytes));
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, n, 0, 63));
+    CUDA_OK(cudaMalloc(&N.child, sizeof(int2) * (size_t)n));
+    CUDA_OK(cudaMalloc(&N.range, sizeof(int2) * (size_t)n));
+    CUDA_OK(cudaMalloc(&N.parent, sizeof(int) * 2 * (size_t)n));
+    CUDA_OK(cudaMalloc(&N.box, sizeof(DBox) * 2 * (size_t)n));
+    CUDA_OK(cudaMalloc(&N.flag, sizeof(int) * (size_t)n));
+    CUDA_OK(cudaMemset(N.flag, 0, sizeof(int) * (size_t)n));
+    CUDA_OK(cudaMemset(N.parent, 0xFF, sizeof(int) * 2 * (size_t)n));
+    if (n > 1) k_lbvh_hierarchy<<<gb, 256>>>(d_keys2, n, N);
+    k_lbvh_fit<<<gb, 256>>>(d_tbox, d_idx2, n, d_bounds, N);
+    CUDA_OK(cudaMalloc(&d_wide, sizeof(Bvh8Node) * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_wide_bin, sizeof(int) * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_wide_depth, sizeof(int) * (size_t)n));
+    CUDA_OK(cudaMalloc(&d_counters, sizeof(int) * 3));
+    CUDA_OK(cudaMemcpy(d_counters, counters, sizeof(counters), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemset(d_wide_bin, 0, sizeof(int)));           // wide node 0 <-> binary root (node 0)
+    {
+        const int one = 1;
+        CUDA_OK(cudaMemcpy(d_wide_depth, &one, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    for (int begin = 0, end = 1; begin < end;) {                 // one launch per level of the wide tree
+        k_lbvh_collapse<<<(unsigned)((end - begin + 127) / 128), 128>>>(begin, end, n, N, d_recs, d_idx2, d_wide_bin, d_wide_depth, d_wide, d_tris, d_counters);
+        CUDA_OK(cudaMemcpy(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
+        begin = end;
+        end = counters[0];
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMalloc(&s->nodes, sizeof(Bvh8Node) * (size_t)counters[0]));
+    CUDA_OK(cudaMemcpy(s->nodes, d_wide, sizeof(Bvh8Node) * (size_t)counters[0], cudaMemcpyDeviceToDevice));
+    s->tris = reinterpret_cast<float4 *>(d_tris);
+    d_tris = nullptr;
+    s->stats.n_tris = n;
+    s->stats.n_nodes = counters[0];
+    s->stats.node_bytes = (int64_t)sizeof(Bvh8Node) * counters[0];
+    s->stats.tri_bytes = (int64_t)sizeof(TriRecord) * n;
+    s->stats.max_depth = counters[2];
+    s->stats.sah_cost = 0.f;
+    for (int k = 0; k < 3; ++k) { s->stats.bounds_lo[k] = hb[k]; s->stats.bounds_hi[k] = hb[3 + k]; }
+    if (counters[1] != n) e = cudaErrorUnknown;                  // every triangle must have been emitted exactly once
+done:
+    cudaFree(d_verts); cudaFree(d_faces); cudaFree(d_recs); cudaFree(d_tris); cudaFree(d_tbox); cudaFree(d_bounds);
+    cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_tmp);
+    cudaFree(N.child); cudaFree(N.range); cudaFree(N.parent); cudaFree(N.box); cudaFree(N.flag);
+    cudaFree(d_wide); cudaFree(d_wide_bin); cudaFree(d_wide_depth); cudaFree(d_counters);
+    return e;
+}
+
 extern "C" {
 
 const char *iris_last_error(void) { return g_err.c_str(); }
@@ -155,13 +245,30 @@ int iris_scene_create(const float *verts, int64_t n_verts, const int32_t *faces,
     *out = nullptr;
     if (n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!verts || !faces))) return fail(IRIS_ERR_INVALID, "bad mesh arguments");
     if (n_faces > 0x7FFFFFF0ll / 3) return fail(IRIS_ERR_INVALID, "too many faces");
-    if (builder != 0) return fail(IRIS_ERR_INVALID, "builder 1 (on-device LBVH) is not available in this build");
+    if (builder != 0 && builder != 1) return fail(IRIS_ERR_INVALID, "builder must be 0 (host binned SAH) or 1 (on-device LBVH)");
     for (int64_t i = 0; i < 3 * n_faces; ++i)
         if (faces[i] < 0 || faces[i] >= n_verts) return fail(IRIS_ERR_INVALID, "face index out of range");
     CUDA_TRY(cudaSetDevice(device));
     int rc = ensure_device_setup(device);
     if (rc) return rc;
     const auto t0 = std::chrono::steady_clock::now();
+    if (builder == 1 && n_faces > 0) {
+        IrisScene *s = new IrisScene();
+        s->device = device;
+        cudaError_t e = device_bvh_build(verts, n_verts, faces, n_faces, s);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess || 2 * s->stats.max_depth > IRIS_STACK) {
+            const std::string msg = e != cudaSuccess ? std::string("device BVH build: ") + cudaGetErrorString(e)
+                                                     : "device BVH deeper than the traversal stack (" + std::to_string(s->stats.max_depth) + " levels)";
+            cudaFree(s->nodes);
+            cudaFree(s->tris);
+            delete s;
+            return fail(e != cudaSuccess ? IRIS_ERR_CUDA : IRIS_ERR_INVALID, msg);
+        }
+        s->stats.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *out = s;
+        return IRIS_OK;
+    }
     HostBvh hb;
     if (host_bvh_build(verts, n_verts, faces, n_faces, &hb) != 0) return fail(IRIS_ERR_NOMEM, "host BVH build failed");
     if (2 * hb.max_depth > IRIS_STACK) {

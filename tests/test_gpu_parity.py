@@ -89,13 +89,15 @@ def test_intersect_bit_exact_cornell(small):
     assert np.array_equal(p.cpu().numpy(), g["p"]) and np.array_equal(n.cpu().numpy(), g["n"])
 
 
-def test_intersect_bit_exact_room_200k():
+@pytest.mark.parametrize("builder", [0, 1])
+def test_intersect_bit_exact_room_200k(builder):
+    """builder 0 = host binned SAH, 1 = on-device LBVH (the default): same hits, bit for bit."""
     dev = _gpu()
     from iris_b200 import core, scenes
     from oracle.intersect import OracleScene
     sc = scenes.room(200_000, 16, seed=3)
     osc = OracleScene(sc.vertices, sc.faces)
-    scene = core.Scene(sc.vertices, sc.faces, 0)
+    scene = core.Scene(sc.vertices, sc.faces, 0, builder=builder)
     st = scene.stats()
     assert st["n_tris"] == sc.n_tris and st["n_nodes"] > 0
     o, d = _rays_for_parity(sc, osc, 250_000, 2)
@@ -491,3 +493,25 @@ def test_tcgen05_field_kernel_equals_mma_sync_kernel(small):
         core.C.check(lib.iris_set_option(b"field_forward_impl", 1))
         b = core.field_forward(small["tables"], x)
         assert torch.equal(a, b), n
+
+
+def test_device_lbvh_builder_gives_identical_hits():
+    """builder = 1 (Morton LBVH built entirely on the device) must return bit-identical hits: traversal is exact, the builder
+    only changes which boxes are visited."""
+    dev = _gpu()
+    from iris_b200 import core, scenes
+    from oracle.intersect import OracleScene
+    for sc in (scenes.cornell(), scenes.room(200_000, 16, seed=3)):
+        osc = OracleScene(sc.vertices, sc.faces)
+        scene = core.Scene(sc.vertices, sc.faces, 0, builder=1)
+        st = scene.stats()
+        assert st["n_tris"] == sc.n_tris and 0 < st["max_depth"] <= 24 and st["n_nodes"] < sc.n_tris
+        o, d = _rays_for_parity(sc, osc, 60_000, 7)
+        _check_intersect(scene, osc, o, d, dev)
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    for faces in (np.array([[0, 1, 2]], np.int32), np.array([[0, 1, 2], [0, 1, 3]], np.int32), np.array([[0, 1, 2]] * 5, np.int32)):
+        scene = core.Scene(v, faces, 0, builder=1)                      # 1, 2 and 5 (coincident) triangles
+        osc = OracleScene(v, faces)
+        o = np.array([[0.2, 0.2, 1.0], [0.2, -1.0, 0.2], [5, 5, 5]], np.float32)
+        d = np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0]], np.float32)
+        _check_intersect(scene, osc, o, d, dev)

@@ -20,6 +20,10 @@ def main():
     t0 = time.time(); sc = scenes.room(n_tris, 16, seed=0); out["gen_s"] = time.time() - t0
     t0 = time.time(); scene = core.Scene(sc.vertices, sc.faces, 0); out["scene_s"] = time.time() - t0
     out["stats"] = scene.stats()
+    if len(sys.argv) > 2 and sys.argv[2] == "lbvh":
+        t0 = time.time(); scene = core.Scene(sc.vertices, sc.faces, 0, builder=1); out["scene_lbvh_first_s"] = time.time() - t0
+        t0 = time.time(); scene = core.Scene(sc.vertices, sc.faces, 0, builder=1); out["scene_lbvh_second_s"] = time.time() - t0
+        out["stats_lbvh"] = scene.stats()
     H = 256
     t0 = time.time(); slf = sc.slf_dict(H); out["slf_s"] = time.time() - t0
     params = torch.empty(9216 + 27954112).uniform_(-1e-4, 1e-4)
