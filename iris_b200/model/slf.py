@@ -14,17 +14,18 @@ class VoxelSLF(nn.Module):
         self.H = H
         self.voxel_min = voxel_min
         self.voxel_max = voxel_max
-        occ = torch.nonzero(mask)                       # rows (z,y,x) in raster order == torch.where(mask)
-        inds = torch.full((H, H, H), -1, dtype=torch.long)
-        inds[occ[:, 0], occ[:, 1], occ[:, 2]] = torch.arange(len(occ))
-        self.register_buffer("inds", inds)
-        self.register_buffer("radiance", torch.zeros(len(occ), 3))
-        self.register_buffer("count", torch.zeros(len(occ), dtype=torch.long))
+        flat = mask.reshape(-1).bool()
+        n_occ = int(flat.sum())
+        table = torch.full((H * H * H,), -1, dtype=torch.long)
+        table[flat] = torch.arange(n_occ)               # raster order over (z,y,x) == the reference's torch.where(mask) order
+        self.register_buffer("inds", table.view(H, H, H))
+        self.register_buffer("radiance", torch.zeros(n_occ, 3))
+        self.register_buffer("count", torch.zeros(n_occ, dtype=torch.long))
 
     def spatial_idx(self, x):
         """model/slf.py:41-54: table row of the voxel containing x (-1 = empty)."""
-        g = ((x - self.voxel_min) / (self.voxel_max - self.voxel_min) * self.H).long().clamp(0, self.H - 1)
-        return self.inds[g[..., 2], g[..., 1], g[..., 0]]
+        cell = ((x - self.voxel_min) / (self.voxel_max - self.voxel_min) * self.H).long().clamp_(0, self.H - 1)
+        return self.inds.view(-1)[(cell[..., 2] * self.H + cell[..., 1]) * self.H + cell[..., 0]]
 
     def scatter_add(self, x, radiance):
         """model/slf.py:56-61 (baking)."""
