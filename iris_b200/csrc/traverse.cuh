@@ -13,6 +13,10 @@
 #ifndef IRIS_SORT_BLOCK
 #define IRIS_SORT_BLOCK 256   // block size of the kernels that re-order their rays
 #endif
+#ifndef IRIS_POSTPONE_NUM
+#define IRIS_POSTPONE_NUM 1      // postpone the remaining triangles when fewer than NUM/DEN of the lanes that
+#define IRIS_POSTPONE_DEN 5      // entered the triangle phase are still in it
+#endif
 #define IRIS_STACK 48   // one node group + one postponed triangle group per level: 2 * depth <= IRIS_STACK
 
 struct SceneView {
@@ -163,7 +167,7 @@ __device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t
 #endif
         while (tgroup.y != 0u) {
 #if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
-            if (__popc(__activemask()) * 5 < tri_lanes && sp < IRIS_STACK - 1) {
+            if (__popc(__activemask()) * IRIS_POSTPONE_DEN < tri_lanes * IRIS_POSTPONE_NUM && sp < IRIS_STACK - 1) {
                 stack[sp++] = tgroup;
                 break;
             }
