@@ -179,6 +179,17 @@ int iris_trace_indirect(const IrisScene *scene, const IrisShadeParams *params, c
                         int64_t n, int32_t indir_depth, const IrisSampler *sampler, float *L, void *workspace, int64_t workspace_bytes,
                         void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * EmorCRF -- the camera response applied right after the estimator in every trainer (crf/model_crf.py:68-86,
+ * train_emitter.py:191-193): ldr = lerp(crf_c, clip(hdr * exposure, 0, 1)) with crf (3, n_bins) = f0 + weight @ basis sampled on a
+ * regular grid over [0,1].  exposure: (n) with exposure_stride 1, or one value with stride 0.  Backward: d_hdr (n,3) written,
+ * d_crf (3,n_bins) accumulated (zero it first); d_weight = d_crf @ basis^T is a (3,dim) matmul left to the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int iris_crf_forward(const float *hdr, const float *exposure, int32_t exposure_stride, const float *crf, int32_t n_bins, int64_t n,
+                     float *ldr, void *stream);
+int iris_crf_backward(const float *hdr, const float *exposure, int32_t exposure_stride, const float *crf, int32_t n_bins,
+                      const float *d_ldr, int64_t n, float *d_hdr, float *d_crf, void *stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t iris_launch_count(void);
 

@@ -13,6 +13,7 @@
 #include "field_tc5.cuh"
 #include "kernels.cuh"
 #include "wavefront.cuh"
+#include "crf.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -683,6 +684,34 @@ int iris_trace_indirect(const IrisScene *s, const IrisShadeParams *P, const floa
         ProfScope ps(K_WAVE_FINISH, st);
         k_wave_finish<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n, 1, W, L, nullptr);
     }
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ EmorCRF
+int iris_crf_forward(const float *hdr, const float *exposure, int32_t exposure_stride, const float *crf, int32_t n_bins, int64_t n, float *ldr,
+                     void *stream) {
+    if (n < 0 || n_bins < 2 || (exposure_stride != 0 && exposure_stride != 1)) return fail(IRIS_ERR_INVALID, "bad crf arguments");
+    if (n == 0) return IRIS_OK;
+    if (!hdr || !exposure || !crf || !ldr) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_crf_forward<<<(unsigned)((3 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hdr, exposure, exposure_stride, crf, n_bins, n, ldr);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_crf_backward(const float *hdr, const float *exposure, int32_t exposure_stride, const float *crf, int32_t n_bins, const float *d_ldr,
+                      int64_t n, float *d_hdr, float *d_crf, void *stream) {
+    if (n < 0 || n_bins < 2 || n_bins > 4096 || (exposure_stride != 0 && exposure_stride != 1)) return fail(IRIS_ERR_INVALID, "bad crf arguments");
+    if (n == 0) return IRIS_OK;
+    if (!hdr || !exposure || !crf || !d_ldr) return fail(IRIS_ERR_INVALID, "NULL array");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ensure_device_setup(dev);
+    if (rc) return rc;
+    const size_t smem = sizeof(float) * 3 * (size_t)n_bins;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_crf_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<int64_t>((3 * n + 255) / 256, (int64_t)g_sm_count * 4);
+    k_crf_backward<<<grid, 256, smem, (cudaStream_t)stream>>>(hdr, exposure, exposure_stride, crf, n_bins, d_ldr, n, d_hdr, d_crf);
     LAUNCHED();
     return IRIS_OK;
 }

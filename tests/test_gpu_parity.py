@@ -515,3 +515,34 @@ def test_device_lbvh_builder_gives_identical_hits():
         o = np.array([[0.2, 0.2, 1.0], [0.2, -1.0, 0.2], [5, 5, 5]], np.float32)
         d = np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0]], np.float32)
         _check_intersect(scene, osc, o, d, dev)
+
+
+def test_emor_crf_forward_backward():
+    """EmorCRF on the CUDA path against the oracle restatement + autograd: values, d_hdr, d_weight; scalar and per-row
+    exposure; values outside the clip range get zero gradient."""
+    dev = _gpu()
+    from iris_b200.crf import EmorCRF
+    from oracle import crf as OC
+    rng = np.random.default_rng(0)
+    xs = np.linspace(0, 1, 1024, dtype=np.float32)
+    f0 = xs ** (1 / 2.2)
+    basis = np.stack([np.sin((k + 1) * np.pi * xs) * 0.1 / (k + 1) for k in range(11)]).astype(np.float32)
+    crf = EmorCRF(dim=11, tables=(f0, basis)).to(dev)
+    with torch.no_grad():
+        crf.weight.copy_(torch.as_tensor(rng.standard_normal((3, 11)).astype(np.float32) * 0.3))
+    n = 10007
+    hdr_np = (rng.random((n, 3)).astype(np.float32) * 1.6 - 0.2)          # some values below 0 and above 1 after exposure
+    for exposure in (torch.tensor([0.8]), torch.as_tensor(rng.uniform(0.5, 1.5, (n, 1)).astype(np.float32))):
+        hdr = torch.as_tensor(hdr_np).to(dev).requires_grad_(True)
+        ldr = crf(hdr, exposure.to(dev))
+        gw = torch.as_tensor(rng.standard_normal((n, 3)).astype(np.float32))
+        crf.weight.grad = None
+        (ldr * gw.to(dev)).sum().backward()
+        hdr_o = torch.as_tensor(hdr_np).requires_grad_(True)
+        w_o = crf.weight.detach().cpu().clone().requires_grad_(True)
+        ref = OC.emor_forward(hdr_o, exposure, torch.as_tensor(f0)[None], torch.as_tensor(basis), w_o)
+        (ref * gw).sum().backward()
+        assert torch.allclose(ldr.detach().cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(hdr.grad.cpu(), hdr_o.grad, rtol=2e-3, atol=1e-4)    # slope = difference of neighbouring LUT entries
+        assert torch.allclose(crf.weight.grad.cpu(), w_o.grad, rtol=1e-3, atol=1e-4)
+    assert crf(torch.zeros(0, 3, device=dev), torch.tensor([1.0], device=dev)).shape == (0, 3)
