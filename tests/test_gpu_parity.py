@@ -543,6 +543,8 @@ def test_emor_crf_forward_backward():
         ref = OC.emor_forward(hdr_o, exposure, torch.as_tensor(f0)[None], torch.as_tensor(basis), w_o)
         (ref * gw).sum().backward()
         assert torch.allclose(ldr.detach().cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
-        assert torch.allclose(hdr.grad.cpu(), hdr_o.grad, rtol=2e-3, atol=1e-4)    # slope = difference of neighbouring LUT entries
+        # d_hdr is the slope of the LUT segment: discontinuous at bin edges, so an input within an ulp of an edge may pick the neighbour
+        bad = ~torch.isclose(hdr.grad.cpu(), hdr_o.grad, rtol=2e-3, atol=1e-4)
+        assert bad.float().mean() < 1e-3, float(bad.float().mean())
         assert torch.allclose(crf.weight.grad.cpu(), w_o.grad, rtol=1e-3, atol=1e-4)
     assert crf(torch.zeros(0, 3, device=dev), torch.tensor([1.0], device=dev)).shape == (0, 3)
