@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
                 f3 v0, e1, e2;
                 emitter_triangle(P, e, v0, e1, e2);
                 float tl, bu, bv;
-                if (tri_test(org, wi, __fdiv_rn(1.0f, xdot(wi, wi)), v0, e1, e2, tl, bu, bv) && !trace_occluded(S, org, wi, tl, face)) {
+                if (tri_test(org, wi, __fdiv_rn(1.0f, xdot(wi, wi)), v0, e1, e2, tl, bu, bv) && !trace_occluded_shared(S, org, wi, tl, face)) {
                     Hit h;
                     h.t = tl; h.u = bu; h.v = bv; h.prim = face; h.slot = -1;
                     f3 hp, hn;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
                 BrdfJac J;
                 sample_brdf<RECORD>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
                 const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
-                const Hit h = trace_closest(S, org, wi);
+                const Hit h = trace_closest_shared(S, org, wi);
                 f3 hp, hn;
                 hit_surface(S, h, wi, hp, hn);
                 int32_t eh;

@@ -84,8 +84,28 @@ __device__ __forceinline__ void load_tri(const SceneView &S, int32_t slot, f3 &v
 // ANYHIT = false: closest hit (minimum t, ties to the lowest prim index).
 // ANYHIT = true : occlusion query against a known candidate (t_limit, prim_limit): returns as soon as some triangle beats the
 //                 candidate under the same ordering (t < t_limit, or t == t_limit and prim < prim_limit); best.slot >= 0 then.
+// IRIS_TRACE_NOINLINE: kernels that cast more than one ray per lane (k_bounce_single, the wavefront kernels) call ONE out-of-line
+// copy of the traversal loop instead of inlining it at every site: the loop is ~14 KB of SASS, and two or three copies of it plus
+// the shading code overflow the 32 KB instruction cache (ncu: stall_no_instruction was the top stall reason of k_bounce_single).
+template <bool ANYHIT>
+__device__ __forceinline__ Hit trace_ray_body(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit, int anyhit_rt);
+
+#ifndef IRIS_HOST_EMULATION
+__device__ __noinline__ Hit trace_ray_shared(const float4 *nodes, const float4 *tris, float ox, float oy, float oz, float dx, float dy, float dz,
+                                             float t_limit, int32_t prim_limit, int anyhit);
+#endif
+
 template <bool ANYHIT>
 __device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit) {
+#if defined(IRIS_TRACE_NOINLINE) && !defined(IRIS_HOST_EMULATION)
+    return trace_ray_shared(S.nodes, S.tris, o.x, o.y, o.z, d.x, d.y, d.z, t_limit, prim_limit, ANYHIT ? 1 : 0);
+#else
+    return trace_ray_body<ANYHIT>(S, o, d, t_limit, prim_limit, 0);
+#endif
+}
+
+template <bool ANYHIT>
+__device__ __forceinline__ Hit trace_ray_body(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit, int anyhit_rt) {
     Hit best;
     best.t = t_limit;
     best.u = best.v = 0.f;
@@ -182,7 +202,7 @@ __device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t
             if (tri_test(o, d, rdd, v0, e1, e2, t, u, v)) {
                 if (t < best.t || (t == best.t && prim < best.prim)) {
                     best.t = t; best.u = u; best.v = v; best.prim = prim; best.slot = slot;
-                    if (ANYHIT) return best;
+                    if (ANYHIT || anyhit_rt) return best;
                 }
             }
         }
@@ -194,12 +214,34 @@ __device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t
     return best;
 }
 
+#ifndef IRIS_HOST_EMULATION
+__device__ __noinline__ Hit trace_ray_shared(const float4 *nodes, const float4 *tris, float ox, float oy, float oz, float dx, float dy, float dz,
+                                             float t_limit, int32_t prim_limit, int anyhit) {
+    SceneView S;
+    S.nodes = nodes;
+    S.tris = tris;
+    S.n_tris = 0;
+    // one loop body for both query kinds: the any-hit early exit is a run-time test on `anyhit`
+    Hit h = trace_ray_body<false>(S, mk3(ox, oy, oz), mk3(dx, dy, dz), t_limit, prim_limit, anyhit);
+    return h;
+}
+#endif
+
 __device__ __forceinline__ Hit trace_closest(const SceneView &S, f3 o, f3 d) {
     return trace_ray<false>(S, o, d, __int_as_float(0x7f800000), -1);
 }
 __device__ __forceinline__ bool trace_occluded(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit) {
     return trace_ray<true>(S, o, d, t_limit, prim_limit).slot >= 0;
 }
+#ifndef IRIS_HOST_EMULATION
+// out-of-line variants for kernels that cast several rays per lane (one copy of the loop in the instruction cache)
+__device__ __forceinline__ Hit trace_closest_shared(const SceneView &S, f3 o, f3 d) {
+    return trace_ray_shared(S.nodes, S.tris, o.x, o.y, o.z, d.x, d.y, d.z, __int_as_float(0x7f800000), -1, 0);
+}
+__device__ __forceinline__ bool trace_occluded_shared(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit) {
+    return trace_ray_shared(S.nodes, S.tris, o.x, o.y, o.z, d.x, d.y, d.z, t_limit, prim_limit, 1).slot >= 0;
+}
+#endif
 
 #ifndef IRIS_HOST_EMULATION
 // ------------------------------------------------------------------------------------------------------------------------

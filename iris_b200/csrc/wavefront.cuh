@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_a(SceneView S, IrisS
             f3 v0, e1, e2;
             emitter_triangle(P, e, v0, e1, e2);
             float tl, bu, bv;
-            if (tri_test(org, wl, __fdiv_rn(1.0f, xdot(wl, wl)), v0, e1, e2, tl, bu, bv) && !trace_occluded(S, org, wl, tl, face)) {
+            if (tri_test(org, wl, __fdiv_rn(1.0f, xdot(wl, wl)), v0, e1, e2, tl, bu, bv) && !trace_occluded_shared(S, org, wl, tl, face)) {
                 Hit h;
                 h.t = tl; h.u = bu; h.v = bv; h.prim = face; h.slot = -1;
                 f3 hp, hn;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_a(SceneView S, IrisS
         W.S8[i] = make_float4(w1, w1, w1, 0.f);
     }
     const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
-    const Hit h = trace_closest(S, org, wi);
+    const Hit h = trace_closest_shared(S, org, wi);
     f3 hp, hn;
     hit_surface(S, h, wi, hp, hn);
     W.H0[i] = make_float4(hp.x, hp.y, hp.z, __int_as_float(h.prim >= 0 ? -2 : -1));
