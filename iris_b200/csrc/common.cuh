@@ -21,7 +21,11 @@ __device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y 
 __device__ __forceinline__ f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 // NF.normalize: v / max(|v|, 1e-12).  |v|^2 is accumulated as fma(z,z,fma(y,y,x*x)) -- the order torch's CPU vector_norm uses for a
 // 3-vector (checked bit for bit) -- and every step is a single IEEE rounding, so directions match the reference's CPU run.
+#ifdef IRIS_HOST_EMULATION
 __device__ __forceinline__ f3 normalize_nf(f3 a) {
+#else
+__device__ __noinline__ f3 normalize_nf(f3 a) {   // out of line: ~55 SASS instructions (IEEE sqrt + 3 IEEE divisions) x a dozen call sites
+#endif
     const float l = fmaxf(__fsqrt_rn(__fmaf_rn(a.z, a.z, __fmaf_rn(a.y, a.y, __fmul_rn(a.x, a.x)))), 1e-12f);
     return mk3(__fdiv_rn(a.x, l), __fdiv_rn(a.y, l), __fdiv_rn(a.z, l));
 }

@@ -48,7 +48,7 @@ __device__ __forceinline__ void normal_space(f3 n, f3 &t, f3 &b) {
     b = cross(n, t);
 }
 // utils/ops.py:32-44 followed by the frame change of model/brdf.py:32-33
-__device__ __forceinline__ f3 sphere_to_world(float theta, float phi, f3 n) {
+__device__ __noinline__ f3 sphere_to_world(float theta, float phi, f3 n) {
     float st, ct, sp, cp;
     sincosf(theta, &st, &ct);
     sincosf(phi, &sp, &cp);
