@@ -342,13 +342,16 @@ def main():
     if rank == 0:
         clocks.start()
     lib.iris_profile_enable(1)
-    for k in range(14):
+    n_kernels = 0
+    while lib.iris_profile_name(n_kernels):
+        n_kernels += 1
+    for k in range(n_kernels):
         lib.iris_profile_read(k, None, None, 1)
     l0 = lib.iris_launch_count()
     ms, (loss, d_rad, d_par_l1) = timed(False, a.steps)
     launches = lib.iris_launch_count() - l0
     prof = {}
-    for k in range(14):
+    for k in range(n_kernels):
         n_, t_ = core.C.c_i64(), core.C.ctypes.c_double()
         lib.iris_profile_read(k, core.C.ctypes.byref(n_), core.C.ctypes.byref(t_), 1)
         if n_.value:
@@ -370,7 +373,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_bounce_single: 2 of the 3 ray casts + BSDF/emitter/SLF/MIS + record)
+    # ---- roofline of the dominant kernel: k_trace_queue (2 of the 3 ray casts of a sample, through the ray queue); with the
+    #      fused bounce selected (iris_set_option single_impl 0) it is k_bounce_single (the same casts + BSDF/emitter/SLF/MIS + record)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -379,19 +383,21 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     R = ray_bytes(sc.n_tris)
     est_bytes = 3 * R + (2048 if want_par else 1024) + 16 + 72.0 / spp      # `single` estimator (+1024 B of grid-gradient writes with BRDF grads)
-    kb = prof.get("k_bounce_single")
+    kname = "k_trace_queue" if "k_trace_queue" in prof else "k_bounce_single"
+    kb = prof.get(kname)
     roof = None
     if kb:
-        k_bytes = 2 * R + 16 + 24.0 / spp                   # this kernel's share: 2 casts + SLF + pixel out/dL
+        # this kernel's share per sample.  fused: 2 casts + SLF + pixel out/dL.  queue: 2 casts + 2 x (32 B ray in + 16 B hit out)
+        k_bytes = 2 * R + 96 if kname == "k_trace_queue" else 2 * R + 16 + 24.0 / spp
         per_launch_samples = n_samples_rank * a.steps / kb["launches"]
         avg_ms = kb["total_ms"] / kb["launches"]
         ach = per_launch_samples * k_bytes / (avg_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bounce_single")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname)
         except Exception:
             pass
-        roof = dict(bound="hbm", kernel="k_bounce_single", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
+        roof = dict(bound="hbm", kernel=kname, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
                     peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", algorithmic_bytes_per_sample=k_bytes,
                     samples_per_launch=per_launch_samples, avg_launch_ms=avg_ms,
                     step=dict(algorithmic_bytes_per_sample=est_bytes, achieved=value / max(world, 1) * est_bytes / 1e9, frac=value / max(world, 1) * est_bytes / 1e9 / peak),

@@ -42,8 +42,8 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
-enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_COUNT };
-static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish"};
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_SINGLE_GEN, K_TRACE_QUEUE, K_SINGLE_SHADE, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish", "k_single_gen", "k_trace_queue", "k_single_shade"};
 struct ProfSpan { int id; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
@@ -73,6 +73,10 @@ static inline SceneView view_of(const IrisScene *s) {
 
 static int g_sm_count = 0;
 static int g_tc5_ctas = 4;      // tcgen05 kernel: CTAs per SM (34.9 KB smem, 64 TMEM columns each)
+static int g_single_impl = 1;      // 1: wavefront bounce (k_single_gen -> k_trace_queue -> k_single_shade), 0: fused k_bounce_single
+static int64_t g_single_chunk = 8 << 20;   // samples per wavefront chunk
+static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
+static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
 static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
 static bool g_field_ready[64] = {false};
 static int ensure_device_setup(int device) {
@@ -192,6 +196,10 @@ int64_t iris_launch_count(void) { return g_launches.load(); }
 
 int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "field_forward_impl") == 0 && (value == 0 || value == 1)) { g_field_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "intersect_impl") == 0 && (value == 0 || value == 1)) { g_intersect_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
+    if (name && std::strcmp(name, "persist_ctas_per_sm") == 0 && value >= 1 && value <= 16) { g_persist_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "tc5_ctas_per_sm") == 0 && value >= 1 && value <= 8) { g_tc5_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "field_smem_carveout_pct") == 0 && value >= 0 && value <= 100) {
         // how much of the SM's 228 KB the field kernels ask to be shared memory: the rest is L1, which the hash-grid gathers live on
@@ -323,7 +331,16 @@ int iris_intersect(const IrisScene *s, const float *o, const float *d, int64_t n
     if (!o || !d) return fail(IRIS_ERR_INVALID, "ray arrays are NULL");
     {
         ProfScope ps(K_INTERSECT, (cudaStream_t)stream);
-        k_intersect<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+        if (g_intersect_impl == 1) {
+            void *cnt = nullptr;
+            CUDA_TRY(cudaGetSymbolAddress(&cnt, g_ray_counter));
+            CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+            const int64_t want = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
+            const int grid = (int)std::min<int64_t>(want, (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
+            k_intersect_persistent<<<grid, IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+        } else {
+            k_intersect<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+        }
     }
     LAUNCHED();
     return IRIS_OK;
@@ -479,9 +496,20 @@ int iris_field_backward(const IrisShadeParams *P, const float *position, const f
     return run_field_backward(P, n, position, nullptr, d_mat, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ray queue of one chunk of the wavefront bounce: counters | rays (2 x 2 float4) | hits (2 float4) | state streams
+static const int64_t SINGLE_MAX_CHUNKS = 1024;
+static int64_t single_chunk_samples(int64_t n) {
+    int64_t c = std::min<int64_t>(n, g_single_chunk);
+    while ((n + c - 1) / c > SINGLE_MAX_CHUNKS) c *= 2;
+    return std::max<int64_t>(c, 1);
+}
+static int64_t single_queue_bytes(int64_t n) {
+    return 8 * SINGLE_MAX_CHUNKS + (4 + 2 + IRIS_SINGLE_STATE_STREAMS) * 16 * single_chunk_samples(n);
+}
+
 int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {
     const int64_t n = n_pixels * (int64_t)spp;
-    const int64_t fwd = 3 * 16 * n;                                                  // w0,w1,w2
+    const int64_t fwd = 3 * 16 * n + single_queue_bytes(n);                          // w0,w1,w2 | ray queue of one chunk
     const int64_t bwd = ((5 * 4 * n + 15) / 16) * 16 + iris_field_backward_workspace_bytes(n);   // d_mat | activation streams of one chunk
     return std::max(fwd, bwd);
 }
@@ -509,10 +537,40 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
     LAUNCHED();
     rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st);
     if (rc) return rc;
-    ProfScope ps(K_BOUNCE_SINGLE, st);
-    if (record) k_bounce_single<true><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, reinterpret_cast<float4 *>(record));
-    else k_bounce_single<false><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, nullptr);
-    LAUNCHED();
+    if (g_single_impl == 0) {
+        ProfScope ps(K_BOUNCE_SINGLE, st);
+        if (record) k_bounce_single<true><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, reinterpret_cast<float4 *>(record));
+        else k_bounce_single<false><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1, w2, L, nullptr);
+        LAUNCHED();
+        return IRIS_OK;
+    }
+    // wavefront bounce: generate rays -> persistent trace -> shade, in chunks whose queue stays small
+    const int64_t nc_max = single_chunk_samples(n);
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(w2 + n);
+    float4 *ro = reinterpret_cast<float4 *>(counters + SINGLE_MAX_CHUNKS), *rd = ro + 2 * nc_max, *hit = rd + 2 * nc_max, *state = hit + 2 * nc_max;
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * SINGLE_MAX_CHUNKS, st));
+    int chunk = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += nc_max, ++chunk) {
+        const int64_t nc = std::min(nc_max, n - i0);
+        {
+            ProfScope ps(K_SINGLE_GEN, st);
+            if (record) k_single_gen<true><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
+            else k_single_gen<false><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
+        }
+        LAUNCHED();
+        {
+            ProfScope ps(K_TRACE_QUEUE, st);
+            const int grid = (int)std::min<int64_t>(blocks_for(2 * nc), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
+            k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, 2 * nc, nc, hit, counters + chunk);
+        }
+        LAUNCHED();
+        {
+            ProfScope ps(K_SINGLE_SHADE, st);
+            if (record) k_single_shade<true><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, reinterpret_cast<float4 *>(record));
+            else k_single_shade<false><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, nullptr);
+        }
+        LAUNCHED();
+    }
     return IRIS_OK;
 }
 

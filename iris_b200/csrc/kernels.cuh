@@ -25,6 +25,59 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_intersect(SceneView S, const flo
     }
 }
 
+// Persistent variant: a fixed grid of warps pulls rays from a global counter; whenever fewer than IRIS_PERSIST_THRESH lanes of a
+// warp still traverse, the finished lanes write their hit and fetch the next rays (Aila & Laine 2009, "dynamic fetch").
+#ifndef IRIS_PERSIST_THRESH
+#define IRIS_PERSIST_THRESH 20
+#endif
+__device__ unsigned long long g_ray_counter;
+
+__global__ void __launch_bounds__(IRIS_BLOCK) k_intersect_persistent(SceneView S, const float *__restrict__ o, const float *__restrict__ d, int64_t n,
+                                                                      float *t, int32_t *prim, float *uv, float *p, float *nrm) {
+    uint2 stack[IRIS_STACK];
+    TravState T;
+    T.done = true;
+    int64_t ray = -1;
+    const unsigned lane = threadIdx.x & 31u;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, T.done);
+        if (T.done && ray >= 0) {
+            const Hit h = T.best;
+            if (t) t[ray] = h.t;
+            if (prim) prim[ray] = h.prim;
+            if (uv) { uv[2 * ray] = h.prim >= 0 ? h.u : 0.f; uv[2 * ray + 1] = h.prim >= 0 ? h.v : 0.f; }
+            if (p || nrm) {
+                f3 hp, hn;
+                hit_surface(S, h, T.d, hp, hn);
+                if (p) st3(p, ray, hp);
+                if (nrm) st3(nrm, ray, hn);
+            }
+            ray = -1;
+        }
+        if (need && !exhausted) {
+            const int cnt = __popc(need), leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(&g_ray_counter, (unsigned long long)cnt);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (T.done) {
+                const int64_t r = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                if (r < n) {
+                    ray = r;
+                    trav_init(T, ld3(o, r), ld3(d, r), __int_as_float(0x7f800000), -1, 0);
+                }
+            }
+            if ((int64_t)base + cnt >= n) exhausted = true;
+        }
+        unsigned active = __ballot_sync(0xffffffffu, !T.done);
+        if (active == 0u) break;
+        do {
+            if (!T.done) trav_step(S, T, stack);
+            active = __ballot_sync(0xffffffffu, !T.done);
+        } while (active != 0u && (exhausted || __popc(active) >= IRIS_PERSIST_THRESH));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ per-pixel mean over spp
 // Lanes of one pixel are consecutive.  Segmented inclusive scan inside the warp, then the last lane of every segment
 // adds the segment sum (already scaled by 1/spp) to the pixel: one atomic per (warp, pixel) pair.
@@ -142,6 +195,223 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_primary(SceneView S, IrisShadePa
 #ifndef IRIS_BOUNCE_MINBLOCKS
 #define IRIS_BOUNCE_MINBLOCKS 5
 #endif
+// ------------------------------------------------------------------------------------------------ ray queue
+// Wavefront form of the secondary bounce: a generator kernel writes rays, ONE small persistent kernel traces them with dynamic
+// fetch (finished lanes pull the next ray, so warps stay full on incoherent rays and the loop fits the instruction cache), and a
+// shading kernel consumes the hits.  A ray is two float4: (origin, t_limit) and (direction, prim_limit); t_limit < 0 marks an
+// empty slot.  Rays [0, n_anyhit) are occlusion queries against the candidate (t_limit, prim_limit), the rest closest-hit.
+// A hit is one float4 (t, u, v, slot); slot < 0 = miss / unoccluded.
+__global__ void __launch_bounds__(IRIS_BLOCK) k_trace_queue(SceneView S, const float4 *__restrict__ ro, const float4 *__restrict__ rd, int64_t n_rays,
+                                                             int64_t n_anyhit, float4 *__restrict__ hit, unsigned long long *counter) {
+    uint2 stack[IRIS_STACK];
+    TravState T;
+    T.done = true;
+    int64_t ray = -1;
+    const unsigned lane = threadIdx.x & 31u;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, T.done);
+        if (T.done && ray >= 0) {
+            hit[ray] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.slot));
+            ray = -1;
+        }
+        if (need && !exhausted) {
+            const int cnt = __popc(need), leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (T.done) {
+                const int64_t r = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                if (r < n_rays) {
+                    const float4 a = ro[r];
+                    if (a.w >= 0.f) {
+                        const float4 b = rd[r];
+                        ray = r;
+                        trav_init(T, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, __float_as_int(b.w), r < n_anyhit ? 1 : 0);
+                    } else {
+                        hit[r] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                    }
+                }
+            }
+            if ((int64_t)base + cnt >= n_rays) exhausted = true;
+        }
+        unsigned active = __ballot_sync(0xffffffffu, !T.done);
+        if (active == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        do {
+            if (!T.done) trav_step(S, T, stack);
+            active = __ballot_sync(0xffffffffu, !T.done);
+        } while (active != 0u && (exhausted || __popc(active) >= IRIS_PERSIST_THRESH));
+    }
+}
+
+// Queue hit -> Hit + surface point / normal (one triangle record load).
+__device__ __forceinline__ Hit queue_hit_surface(const SceneView &S, float4 q, f3 d, f3 &p, f3 &n) {
+    Hit h;
+    h.t = q.x; h.u = q.y; h.v = q.z;
+    h.slot = __float_as_int(q.w);
+    h.prim = -1;
+    p = mk3(0.f, 0.f, 0.f);
+    n = p;
+    if (h.slot >= 0) {
+        f3 v0, e1, e2;
+        load_tri(S, h.slot, v0, e1, e2, h.prim);
+        surface_from_triangle(h, d, v0, e1, e2, p, n);
+    }
+    return h;
+}
+
+// path_tracing_single, generator half: everything of utils/path_tracing.py:359-404 that does not depend on a ray cast.
+// Per-sample state streams (float4, chunk-local index j, stride nc):
+//   s0 = (L_nee.rgb if unoccluded, pdf_b)   s1 = (wb.rgb, e_nee)                      e_nee < 0: no shadow ray
+//   RECORD: s2 = (c_nee.rgb, JaN.x) s3 = (JaN.yz, JrN.xy) s4 = (JrN.z, JmN.xyz) s5 = (Jb.da, Jb.dr.x) s6 = (Jb.dr.yz, Jb.dm.xy) s7 = (Jb.dm.z,..)
+#define IRIS_SINGLE_STATE_STREAMS 8
+template <bool RECORD>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays, int64_t i0, int64_t nc, int spp,
+                                                            const float4 *__restrict__ w0, const float4 *__restrict__ w1, const float4 *__restrict__ w2,
+                                                            float4 *__restrict__ ro, float4 *__restrict__ rd, float4 *__restrict__ st) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nc) return;
+    const int64_t i = i0 + j;
+    const float4 a = w0[i];
+    float4 ro_s = make_float4(0.f, 0.f, 0.f, -1.f), rd_s = ro_s, ro_b = ro_s, rd_b = ro_s;
+    if (__float_as_int(a.w) == -2) {
+        const float4 b = w1[i], c = w2[i];
+        const f3 x0 = mk3(a.x, a.y, a.z), n0 = mk3(b.x, b.y, b.z);
+        Mat mat;
+        mat.a = mk3(c.x, c.y, c.z);
+        mat.r = c.w;
+        mat.m = b.w;
+        const float4 ua = sample4(smp, i, 0), ub = sample4(smp, i, 1);
+        const f3 wo = -camera_dir(rays, i / spp, ua.x, ua.y);
+        int32_t e_nee = -1;
+        f3 L_nee = mk3(0.f, 0.f, 0.f), c_nee = L_nee, JaN = L_nee, JrN = L_nee, JmN = L_nee;
+        {   // emitter sample: the contribution if the shadow ray comes back unoccluded (see k_bounce_single for the equivalence)
+            f3 wi;
+            float pdf_e;
+            int32_t e, face;
+            sample_emitter(P, ua.z, ua.w, ub.x, x0, wi, pdf_e, e, face);
+            const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+            f3 v0, e1, e2;
+            emitter_triangle(P, e, v0, e1, e2);
+            float tl, bu, bv;
+            if (tri_test(org, wi, __fdiv_rn(1.0f, xdot(wi, wi)), v0, e1, e2, tl, bu, bv)) {
+                ro_s = make_float4(org.x, org.y, org.z, tl);
+                rd_s = make_float4(wi.x, wi.y, wi.z, __int_as_float(face));
+                Hit h;
+                h.t = tl; h.u = bu; h.v = bv; h.prim = face; h.slot = -1;
+                f3 hp, hn;
+                surface_from_triangle(h, wi, v0, e1, e2, hp, hn);
+                const f3 dlt = hp - x0;
+                const float G = fabsf(-(wi.x * hn.x) - (wi.y * hn.y) - (wi.z * hn.z)) / fmaxf(dot(dlt, dlt), 1e-6f);
+                f3 f;
+                float pdf_b;
+                BrdfJac J;
+                eval_brdf<RECORD>(wi, wo, n0, mat, f, pdf_b, &J);
+                pdf_b *= G;
+                float w = (pdf_e > 0.f && !isinf(pdf_b)) ? pdf_e * pdf_e / fmaxf(pdf_e * pdf_e + pdf_b * pdf_b, 1e-6f) : 0.f;
+                if (isinf(pdf_e) || pdf_b == 0.f) w = 1.f;
+                const float s = G / fmaxf(pdf_e, 1e-6f) * w;
+                const f3 W = emitter_radiance(P, e) * s;
+                L_nee = f * W;
+                e_nee = e;
+                if (RECORD) {
+                    c_nee = f * s;
+                    JaN = J.da * W; JrN = J.dr * W; JmN = J.dm * W;
+                }
+            }
+        }
+        f3 wi, wb;
+        float pdf_b;
+        BrdfJac J;
+        sample_brdf<RECORD>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
+        ro_b = make_float4(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
+        rd_b = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
+        st[j] = make_float4(L_nee.x, L_nee.y, L_nee.z, pdf_b);
+        st[nc + j] = make_float4(wb.x, wb.y, wb.z, __int_as_float(e_nee));
+        if (RECORD) {
+            st[2 * nc + j] = make_float4(c_nee.x, c_nee.y, c_nee.z, JaN.x);
+            st[3 * nc + j] = make_float4(JaN.y, JaN.z, JrN.x, JrN.y);
+            st[4 * nc + j] = make_float4(JrN.z, JmN.x, JmN.y, JmN.z);
+            st[5 * nc + j] = make_float4(J.da.x, J.da.y, J.da.z, J.dr.x);
+            st[6 * nc + j] = make_float4(J.dr.y, J.dr.z, J.dm.x, J.dm.y);
+            st[7 * nc + j] = make_float4(J.dm.z, 0.f, 0.f, 0.f);
+        }
+    }
+    ro[j] = ro_s; rd[j] = rd_s;
+    ro[nc + j] = ro_b; rd[nc + j] = rd_b;
+}
+
+// path_tracing_single, shading half: visibility, emitter / SLF radiance at the BSDF hit, MIS, the adjoint record, pixel mean.
+template <bool RECORD>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_single_shade(SceneView S, IrisShadeParams P, int64_t i0, int64_t nc, int64_t n, int spp,
+                                                              const float4 *__restrict__ w0, const float4 *__restrict__ rd, const float4 *__restrict__ hit,
+                                                              const float4 *__restrict__ st, float *L_out, float4 *__restrict__ rec) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = j < nc;
+    const int64_t i = i0 + j;
+    const int64_t pix = in_range ? i / spp : 0;
+    f3 L = mk3(0.f, 0.f, 0.f);
+    if (in_range) {
+        const float4 a = w0[i];
+        const int code = __float_as_int(a.w);
+        int32_t e0 = -1, e_nee = -1, e_b = -1;
+        f3 c_nee = mk3(0.f, 0.f, 0.f), c_b = mk3(0.f, 0.f, 0.f);
+        f3 Ja = c_nee, Jr = c_nee, Jm = c_nee;
+        if (code >= 0) {
+            e0 = code;
+            L = emitter_radiance(P, e0);
+        } else if (code == -2) {
+            const f3 x0 = mk3(a.x, a.y, a.z);
+            const float4 s0 = st[j], s1 = st[nc + j];
+            if (__float_as_int(s1.w) >= 0 && __float_as_int(hit[j].w) < 0) {
+                L = mk3(s0.x, s0.y, s0.z);
+                if (RECORD) {
+                    const float4 s2 = st[2 * nc + j], s3 = st[3 * nc + j], s4 = st[4 * nc + j];
+                    e_nee = __float_as_int(s1.w);
+                    c_nee = mk3(s2.x, s2.y, s2.z);
+                    Ja = mk3(s2.w, s3.x, s3.y); Jr = mk3(s3.z, s3.w, s4.x); Jm = mk3(s4.y, s4.z, s4.w);
+                }
+            }
+            const float4 dq = rd[nc + j];
+            const f3 wi = mk3(dq.x, dq.y, dq.z), wb = mk3(s1.x, s1.y, s1.z);
+            float pdf_b = s0.w;
+            f3 hp, hn;
+            const Hit h = queue_hit_surface(S, hit[nc + j], wi, hp, hn);
+            int32_t eh;
+            float pdf_e;
+            bool vn;
+            const f3 Le = radiance_at_hit(P, h, hp, eh, pdf_e, vn);
+            float G = 1.f;
+            if (vn) {
+                const f3 dlt = x0 - hp;
+                G = fabsf(-(hn.x * wi.x) - (hn.y * wi.y) - (hn.z * wi.z)) / fmaxf(dot(dlt, dlt), 1e-6f);
+            }
+            pdf_b *= G;
+            float w = (pdf_b > 0.f && !isinf(pdf_e)) ? pdf_b * pdf_b / (pdf_e * pdf_e + pdf_b * pdf_b) : 0.f;
+            if (isinf(pdf_b) || pdf_e == 0.f) w = 1.f;
+            L = L + wb * Le * w;
+            if (RECORD) {
+                const float4 s5 = st[5 * nc + j], s6 = st[6 * nc + j], s7 = st[7 * nc + j];
+                if (eh >= 0) { e_b = eh; c_b = wb * w; }
+                const f3 Lw = Le * w;
+                Ja = Ja + mk3(s5.x, s5.y, s5.z) * Lw; Jr = Jr + mk3(s5.w, s6.x, s6.y) * Lw; Jm = Jm + mk3(s6.z, s6.w, s7.x) * Lw;
+            }
+        }
+        if (RECORD) {
+            rec[i] = make_float4(__int_as_float(e0), __int_as_float(e_nee), __int_as_float(e_b), 0.f);
+            rec[n + i] = make_float4(c_nee.x, c_nee.y, c_nee.z, c_b.x);
+            rec[2 * n + i] = make_float4(c_b.y, c_b.z, Ja.x, Ja.y);
+            rec[3 * n + i] = make_float4(Ja.z, Jr.x, Jr.y, Jr.z);
+            rec[4 * n + i] = make_float4(Jm.x, Jm.y, Jm.z, 0.f);
+            rec[5 * n + i] = a;
+        }
+    }
+    pixel_accumulate(L_out, pix, in_range, L, 1.f / (float)spp);
+}
+
 template <bool RECORD>
 __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_single(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
                                                                int64_t n_pixels, int spp, const float4 *__restrict__ w0,

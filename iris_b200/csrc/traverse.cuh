@@ -104,114 +104,136 @@ __device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t
 #endif
 }
 
-template <bool ANYHIT>
-__device__ __forceinline__ Hit trace_ray_body(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit, int anyhit_rt) {
+// Traversal as explicit state + step, so that the same code serves the one-ray-per-lane loop (trace_ray_body) and the persistent
+// kernel that refills finished lanes with new rays (k_trace_persistent).
+struct TravState {
+    f3 o, d;
+    float sx, sy, sz, idx, idy, idz, rdd;
+    uint32_t octinv;
+    uint2 ngroup, tgroup;
+    int sp;
+    int anyhit;
+    bool done;
     Hit best;
-    best.t = t_limit;
-    best.u = best.v = 0.f;
-    best.prim = prim_limit;
-    best.slot = -1;
+};
 
-    uint2 stack[IRIS_STACK];
-    int sp = 0;
+__device__ __forceinline__ void trav_init(TravState &T, f3 o, f3 d, float t_limit, int32_t prim_limit, int anyhit) {
+    T.o = o;
+    T.d = d;
+    T.best.t = t_limit;
+    T.best.u = T.best.v = 0.f;
+    T.best.prim = prim_limit;
+    T.best.slot = -1;
+    T.sp = 0;
+    T.anyhit = anyhit;
+    T.done = false;
+    T.sx = fabsf(d.x) < 1e-30f ? copysignf(1e-30f, d.x) : d.x;
+    T.sy = fabsf(d.y) < 1e-30f ? copysignf(1e-30f, d.y) : d.y;
+    T.sz = fabsf(d.z) < 1e-30f ? copysignf(1e-30f, d.z) : d.z;
+    T.idx = 1.0f / T.sx;
+    T.idy = 1.0f / T.sy;
+    T.idz = 1.0f / T.sz;
+    T.octinv = (T.sx < 0.f ? 0u : 4u) | (T.sy < 0.f ? 0u : 2u) | (T.sz < 0.f ? 0u : 1u);
+    T.rdd = __fdiv_rn(1.0f, xdot(d, d));
+    T.ngroup = make_uint2(0u, 0x80000000u);
+    T.tgroup = make_uint2(0u, 0u);
+}
 
-    const float sx = fabsf(d.x) < 1e-30f ? copysignf(1e-30f, d.x) : d.x;
-    const float sy = fabsf(d.y) < 1e-30f ? copysignf(1e-30f, d.y) : d.y;
-    const float sz = fabsf(d.z) < 1e-30f ? copysignf(1e-30f, d.z) : d.z;
-    const float idx = 1.0f / sx, idy = 1.0f / sy, idz = 1.0f / sz;
-    const uint32_t octinv = (sx < 0.f ? 0u : 4u) | (sy < 0.f ? 0u : 2u) | (sz < 0.f ? 0u : 1u);
-    const uint32_t octinv4 = octinv * 0x01010101u;
-    const float rdd = __fdiv_rn(1.0f, xdot(d, d));
-
-    uint2 ngroup = make_uint2(0u, 0x80000000u);
-    uint2 tgroup = make_uint2(0u, 0u);
-
-    while (true) {
-        if (ngroup.y > 0x00FFFFFFu) {
-            const uint32_t hits = ngroup.y;
-            const uint32_t imask = ngroup.y;
-            const uint32_t bit = 31u - __clz(hits);
-            const uint32_t base = ngroup.x;
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00FFFFFFu) {
-                stack[sp++] = ngroup;   // depth <= IRIS_STACK is checked when the scene is built
-            }
-            const uint32_t slot = (bit - 24u) ^ octinv;
-            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const float4 *np = S.nodes + 5 * (int64_t)(base + rel);
-            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
-            const uint32_t ew = __float_as_uint(n0.w);
-            ngroup.x = __float_as_uint(n1.x);
-            tgroup.x = __float_as_uint(n1.y);
-            const float ax = __uint_as_float((ew & 0xFFu) << 23) * idx;
-            const float ay = __uint_as_float(((ew >> 8) & 0xFFu) << 23) * idy;
-            const float az = __uint_as_float(((ew >> 16) & 0xFFu) << 23) * idz;
-            const float bx = (n0.x - o.x) * idx, by = (n0.y - o.y) * idy, bz = (n0.z - o.z) * idz;
-            uint32_t hitmask = 0u;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
-                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-                const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlx = __float_as_uint(h ? n2.y : n2.x), qly = __float_as_uint(h ? n2.w : n2.z), qlz = __float_as_uint(h ? n3.y : n3.x);
-                const uint32_t qhx = __float_as_uint(h ? n3.w : n3.z), qhy = __float_as_uint(h ? n4.y : n4.x), qhz = __float_as_uint(h ? n4.w : n4.z);
-                const uint32_t nx = sx < 0.f ? qhx : qlx, fx = sx < 0.f ? qlx : qhx;
-                const uint32_t ny = sy < 0.f ? qhy : qly, fy = sy < 0.f ? qly : qhy;
-                const uint32_t nz = sz < 0.f ? qhz : qlz, fz = sz < 0.f ? qlz : qhz;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
-                    const float t0y = fmaf(byte_f(ny, j), ay, by), t1y = fmaf(byte_f(fy, j), ay, by);
-                    const float t0z = fmaf(byte_f(nz, j), az, bz), t1z = fmaf(byte_f(fz, j), az, bz);
-                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best.t));
-                    if (tn <= tf) {
-                        const uint32_t cb = (child_bits4 >> (8 * j)) & 0xFFu;
-                        const uint32_t bi = (bit_index4 >> (8 * j)) & 0xFFu;
-                        hitmask |= cb << bi;
-                    }
-                }
-            }
-            ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
-            tgroup.y = hitmask & 0x00FFFFFFu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
+// One iteration: at most one node, then this lane's pending triangles (with postponing), then a pop.  Sets T.done.
+__device__ __forceinline__ void trav_step(const SceneView &S, TravState &T, uint2 *stack) {
+    const uint32_t octinv4 = T.octinv * 0x01010101u;
+    if (T.ngroup.y > 0x00FFFFFFu) {
+        const uint32_t hits = T.ngroup.y;
+        const uint32_t imask = T.ngroup.y;
+        const uint32_t bit = 31u - __clz(hits);
+        const uint32_t base = T.ngroup.x;
+        T.ngroup.y &= ~(1u << bit);
+        if (T.ngroup.y > 0x00FFFFFFu) {
+            stack[T.sp++] = T.ngroup;   // depth <= IRIS_STACK is checked when the scene is built
         }
-#if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
-        // triangle postponing (Ylitie et al. 2017): when fewer than ~20% of the lanes that entered the triangle phase are
-        // still testing triangles, the stragglers park their remaining triangles on the stack and go back to node work
-        const int tri_lanes = __popc(__activemask());
-#endif
-        while (tgroup.y != 0u) {
-#if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
-            if (__popc(__activemask()) * IRIS_POSTPONE_DEN < tri_lanes * IRIS_POSTPONE_NUM && sp < IRIS_STACK - 1) {
-                stack[sp++] = tgroup;
-                break;
-            }
-#endif
-            const uint32_t ti = 31u - __clz(tgroup.y);
-            tgroup.y &= ~(1u << ti);
-            const int32_t slot = (int32_t)(tgroup.x + ti);
-            f3 v0, e1, e2;
-            int32_t prim;
-            load_tri(S, slot, v0, e1, e2, prim);
-            float t, u, v;
-            if (tri_test(o, d, rdd, v0, e1, e2, t, u, v)) {
-                if (t < best.t || (t == best.t && prim < best.prim)) {
-                    best.t = t; best.u = u; best.v = v; best.prim = prim; best.slot = slot;
-                    if (ANYHIT || anyhit_rt) return best;
+        const uint32_t slot = (bit - 24u) ^ T.octinv;
+        const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+        const float4 *np = S.nodes + 5 * (int64_t)(base + rel);
+        const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
+        const uint32_t ew = __float_as_uint(n0.w);
+        T.ngroup.x = __float_as_uint(n1.x);
+        T.tgroup.x = __float_as_uint(n1.y);
+        const float ax = __uint_as_float((ew & 0xFFu) << 23) * T.idx;
+        const float ay = __uint_as_float(((ew >> 8) & 0xFFu) << 23) * T.idy;
+        const float az = __uint_as_float(((ew >> 16) & 0xFFu) << 23) * T.idz;
+        const float bx = (n0.x - T.o.x) * T.idx, by = (n0.y - T.o.y) * T.idy, bz = (n0.z - T.o.z) * T.idz;
+        uint32_t hitmask = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
+            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlx = __float_as_uint(h ? n2.y : n2.x), qly = __float_as_uint(h ? n2.w : n2.z), qlz = __float_as_uint(h ? n3.y : n3.x);
+            const uint32_t qhx = __float_as_uint(h ? n3.w : n3.z), qhy = __float_as_uint(h ? n4.y : n4.x), qhz = __float_as_uint(h ? n4.w : n4.z);
+            const uint32_t nx = T.sx < 0.f ? qhx : qlx, fx = T.sx < 0.f ? qlx : qhx;
+            const uint32_t ny = T.sy < 0.f ? qhy : qly, fy = T.sy < 0.f ? qly : qhy;
+            const uint32_t nz = T.sz < 0.f ? qhz : qlz, fz = T.sz < 0.f ? qlz : qhz;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
+                const float t0y = fmaf(byte_f(ny, j), ay, by), t1y = fmaf(byte_f(fy, j), ay, by);
+                const float t0z = fmaf(byte_f(nz, j), az, bz), t1z = fmaf(byte_f(fz, j), az, bz);
+                const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                const float tf = fminf(fminf(t1x, t1y), fminf(t1z, T.best.t));
+                if (tn <= tf) {
+                    const uint32_t cb = (child_bits4 >> (8 * j)) & 0xFFu;
+                    const uint32_t bi = (bit_index4 >> (8 * j)) & 0xFFu;
+                    hitmask |= cb << bi;
                 }
             }
         }
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (sp == 0) break;
-            ngroup = stack[--sp];
+        T.ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
+        T.tgroup.y = hitmask & 0x00FFFFFFu;
+    } else {
+        T.tgroup = T.ngroup;
+        T.ngroup = make_uint2(0u, 0u);
+    }
+#if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
+    // triangle postponing (Ylitie et al. 2017): when fewer than ~20% of the lanes that entered the triangle phase are
+    // still testing triangles, the stragglers park their remaining triangles on the stack and go back to node work
+    const int tri_lanes = __popc(__activemask());
+#endif
+    while (T.tgroup.y != 0u) {
+#if !defined(IRIS_HOST_EMULATION) && !defined(IRIS_NO_POSTPONE)
+        if (__popc(__activemask()) * IRIS_POSTPONE_DEN < tri_lanes * IRIS_POSTPONE_NUM && T.sp < IRIS_STACK - 1) {
+            stack[T.sp++] = T.tgroup;
+            break;
+        }
+#endif
+        const uint32_t ti = 31u - __clz(T.tgroup.y);
+        T.tgroup.y &= ~(1u << ti);
+        const int32_t slot = (int32_t)(T.tgroup.x + ti);
+        f3 v0, e1, e2;
+        int32_t prim;
+        load_tri(S, slot, v0, e1, e2, prim);
+        float t, u, v;
+        if (tri_test(T.o, T.d, T.rdd, v0, e1, e2, t, u, v)) {
+            if (t < T.best.t || (t == T.best.t && prim < T.best.prim)) {
+                T.best.t = t; T.best.u = u; T.best.v = v; T.best.prim = prim; T.best.slot = slot;
+                if (T.anyhit) { T.done = true; return; }
+            }
         }
     }
-    return best;
+    if (T.ngroup.y <= 0x00FFFFFFu) {
+        if (T.sp == 0) { T.done = true; return; }
+        T.ngroup = stack[--T.sp];
+    }
+}
+
+template <bool ANYHIT>
+__device__ __forceinline__ Hit trace_ray_body(const SceneView &S, f3 o, f3 d, float t_limit, int32_t prim_limit, int anyhit_rt) {
+    TravState T;
+    uint2 stack[IRIS_STACK];
+    trav_init(T, o, d, t_limit, prim_limit, (ANYHIT || anyhit_rt) ? 1 : 0);
+    while (!T.done) trav_step(S, T, stack);
+    return T.best;
 }
 
 #ifndef IRIS_HOST_EMULATION

@@ -495,6 +495,50 @@ def test_tcgen05_field_kernel_equals_mma_sync_kernel(small):
         assert torch.equal(a, b), n
 
 
+def test_wavefront_bounce_equals_fused_bounce(small):
+    """path_tracing_single's secondary bounce runs as generate -> persistent ray-queue trace -> shade by default; the fused
+    one-kernel form is kept behind a switch.  Same arithmetic, same rays: the adjoint record must be bit-identical, and the
+    image equal up to the order of the per-pixel float atomics.  Chunk sizes smaller than the launch exercise the chunk loop."""
+    from iris_b200 import core
+    lib = core.C.lib()
+    try:
+        core.C.check(lib.iris_set_option(b"single_impl", 0))
+        L0, rec0 = _single(small, True)
+        for log2 in (10, 21):
+            core.C.check(lib.iris_set_option(b"single_impl", 1))
+            core.C.check(lib.iris_set_option(b"single_chunk_log2", log2))
+            L1, rec1 = _single(small, True)
+            L2, _ = _single(small, False)
+            assert torch.equal(rec0.view(torch.int32), rec1.view(torch.int32)), log2
+            assert torch.allclose(L0, L1, rtol=1e-5, atol=1e-7) and torch.allclose(L1, L2, rtol=1e-5, atol=1e-7), log2
+    finally:
+        core.C.check(lib.iris_set_option(b"single_impl", 1))
+        core.C.check(lib.iris_set_option(b"single_chunk_log2", 23))
+
+
+def test_persistent_intersect_equals_static_intersect():
+    """ray_intersect with dynamic ray fetch (intersect_impl = 1) returns bit-identical hits."""
+    dev = _gpu()
+    from iris_b200 import core, scenes
+    lib = core.C.lib()
+    sc = scenes.room(20000, 4, seed=5)
+    scene = core.Scene(sc.vertices, sc.faces, 0)
+    g = torch.Generator().manual_seed(11)
+    lo, hi = torch.tensor(sc.vertices.min(0)), torch.tensor(sc.vertices.max(0))
+    for n in (1, 33, 100003):
+        o = (lo + (hi - lo) * torch.rand(n, 3, generator=g)).float().to(dev)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(dev)
+        try:
+            core.C.check(lib.iris_set_option(b"intersect_impl", 0))
+            a = scene.intersect_raw(o, d)
+            core.C.check(lib.iris_set_option(b"intersect_impl", 1))
+            b = scene.intersect_raw(o, d)
+        finally:
+            core.C.check(lib.iris_set_option(b"intersect_impl", 0))
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), n
+
+
 def test_device_lbvh_builder_gives_identical_hits():
     """builder = 1 (Morton LBVH built entirely on the device) must return bit-identical hits: traversal is exact, the builder
     only changes which boxes are visited."""
