@@ -201,7 +201,10 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_primary(SceneView S, IrisShadePa
 // shading kernel consumes the hits.  A ray is two float4: (origin, t_limit) and (direction, prim_limit); t_limit < 0 marks an
 // empty slot.  Rays [0, n_anyhit) are occlusion queries against the candidate (t_limit, prim_limit), the rest closest-hit.
 // A hit is one float4 (t, u, v, slot); slot < 0 = miss / unoccluded.
-__global__ void __launch_bounds__(IRIS_BLOCK) k_trace_queue(SceneView S, const float4 *__restrict__ ro, const float4 *__restrict__ rd, int64_t n_rays,
+#ifndef IRIS_QUEUE_MINBLOCKS
+#define IRIS_QUEUE_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(IRIS_BLOCK, IRIS_QUEUE_MINBLOCKS) k_trace_queue(SceneView S, const float4 *__restrict__ ro, const float4 *__restrict__ rd, int64_t n_rays,
                                                              int64_t n_anyhit, float4 *__restrict__ hit, unsigned long long *counter) {
     uint2 stack[IRIS_STACK];
     TravState T;

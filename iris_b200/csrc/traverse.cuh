@@ -31,6 +31,10 @@ struct Hit {
     int32_t slot;   // record index in SceneView::tris
 };
 
+#ifndef IRIS_HOST_EMULATION
+__constant__ uint32_t c_byte_magic = 0x4B000000u;
+__constant__ uint32_t c_half_magic = 0x64646464u;
+#endif
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
 #ifdef IRIS_HOST_EMULATION   // tests/host/traverse_host.cpp
     return ((x >> 7) & 0x01010101u) * 0xFFu;
@@ -46,11 +50,37 @@ __device__ __forceinline__ float byte_f(uint32_t w, int j) {
 #ifdef IRIS_HOST_EMULATION
     return (float)((w >> (8 * j)) & 0xFFu);
 #else
+    // the 2^23 pattern comes from constant memory so that it stays a register/constant operand and the byte selector is the
+    // immediate; with both literal, ptxas keeps 0x4B000000 as the immediate and moves the selector into a register per PRMT
     uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(0x7440u + (uint32_t)j));
+    const uint32_t magic = c_byte_magic;
+    switch (j) {   // j is a literal after unrolling
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7440;" : "=r"(r) : "r"(w), "r"(magic)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7441;" : "=r"(r) : "r"(w), "r"(magic)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7442;" : "=r"(r) : "r"(w), "r"(magic)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7443;" : "=r"(r) : "r"(w), "r"(magic)); break;
+    }
     return __uint_as_float(r) - 8388608.0f;
 #endif
 }
+
+#ifndef IRIS_HOST_EMULATION
+// bytes j and j+1 of w (j = 0 or 2) -> out[k] = fma(1024 + q_k, a, c), as one PRMT, two HADD2.F32 and one FFMA2
+__device__ __forceinline__ void slab_pair(uint32_t w, int j, float a, float c, float (&out)[2]) {
+    const uint32_t magic = c_half_magic;
+    uint32_t h2;
+    if (j == 0) asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(h2) : "r"(w), "r"(magic));
+    else asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(h2) : "r"(w), "r"(magic));
+    float v0, v1;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(v0), "=f"(v1) : "r"(h2));
+    unsigned long long v, aa, cc, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(v), "l"(aa), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(out[0]), "=f"(out[1]) : "l"(r));
+}
+#endif
 
 // Moller-Trumbore barycentrics + projected t, operation order of oracle/intersect.c:tri_test (rdd = 1/(d.d))
 __device__ __forceinline__ bool tri_test(f3 o, f3 d, float rdd, f3 v0, f3 e1, f3 e2, float &t, float &u, float &v) {
@@ -175,6 +205,7 @@ __device__ __forceinline__ void trav_step(const SceneView &S, TravState &T, uint
             const uint32_t nx = T.sx < 0.f ? qhx : qlx, fx = T.sx < 0.f ? qlx : qhx;
             const uint32_t ny = T.sy < 0.f ? qhy : qly, fy = T.sy < 0.f ? qly : qhy;
             const uint32_t nz = T.sz < 0.f ? qhz : qlz, fz = T.sz < 0.f ? qlz : qhz;
+#if defined(IRIS_HOST_EMULATION) || defined(IRIS_NODE_SCALAR)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
@@ -188,6 +219,30 @@ __device__ __forceinline__ void trav_step(const SceneView &S, TravState &T, uint
                     hitmask |= cb << bi;
                 }
             }
+#else
+            // Two children per step.  One PRMT turns two quantised bytes into the half2 (1024 + q_j, 1024 + q_j+1) (0x64 is the
+            // high byte of fp16 1024, whose ulp is 1), the two f16 -> f32 conversions and the packed FFMA2 run on the FMA pipe, and
+            // the 1024 is folded into the plane offset (b - 1024 a, one rounding of ~2^-14 quantisation steps).  Against one PRMT +
+            // FADD + FFMA per byte this halves the ALU-pipe work of the slab test, the pipe this loop is bound by.
+            const float cx = fmaf(-1024.0f, ax, bx), cy = fmaf(-1024.0f, ay, by), cz = fmaf(-1024.0f, az, bz);
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                float t0x[2], t1x[2], t0y[2], t1y[2], t0z[2], t1z[2];
+                slab_pair(nx, j, ax, cx, t0x); slab_pair(fx, j, ax, cx, t1x);
+                slab_pair(ny, j, ay, cy, t0y); slab_pair(fy, j, ay, cy, t1y);
+                slab_pair(nz, j, az, cz, t0z); slab_pair(fz, j, az, cz, t1z);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float tn = fmaxf(fmaxf(t0x[k], t0y[k]), fmaxf(t0z[k], 0.0f));
+                    const float tf = fminf(fminf(t1x[k], t1y[k]), fminf(t1z[k], T.best.t));
+                    if (tn <= tf) {
+                        const uint32_t cb = (child_bits4 >> (8 * (j + k))) & 0xFFu;
+                        const uint32_t bi = (bit_index4 >> (8 * (j + k))) & 0xFFu;
+                        hitmask |= cb << bi;
+                    }
+                }
+            }
+#endif
         }
         T.ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
         T.tgroup.y = hitmask & 0x00FFFFFFu;

@@ -22,14 +22,16 @@ def main():
         ws = torch.empty(lib.iris_single_workspace_bytes(rays.shape[0], spp), dtype=torch.uint8, device=dev)
         ms = ev_time(lambda: core.single_forward(scene, tables, rays, spp, smp, rec, ws), 3, 1)
         out[tag] = round(n / ms / 1e3, 1)
+    import os
+    quick = os.environ.get("IRIS_PERF_QUICK") == "1"
     core.C.check(lib.iris_set_option(b"single_impl", 0))
-    run("fused", False); run("fused_rec", True)
+    run("fused_rec", True)
     core.C.check(lib.iris_set_option(b"single_impl", 1))
-    for log2 in (19, 20, 21, 22, 23, 26):
+    for log2 in ((23,) if quick else (19, 20, 21, 22, 23, 26)):
         core.C.check(lib.iris_set_option(b"single_chunk_log2", log2))
         run("wave_c%d" % log2, False); run("wave_rec_c%d" % log2, True)
-    core.C.check(lib.iris_set_option(b"single_chunk_log2", 21))
-    for ctas in (6, 10):
+    core.C.check(lib.iris_set_option(b"single_chunk_log2", 23))
+    for ctas in (() if quick else (6, 10)):
         core.C.check(lib.iris_set_option(b"persist_ctas_per_sm", ctas))
         run("wave_rec_c21_ctas%d" % ctas, True)
     core.C.check(lib.iris_set_option(b"persist_ctas_per_sm", 8))
