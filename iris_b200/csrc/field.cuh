@@ -245,9 +245,11 @@ __device__ __forceinline__ float sigmoid16(float y_acc) {
 
 // WS = true : positions and the continue flag come from the estimator workspace w0, results go to w2 / w1.w
 // WS = false: NGPBRDF.forward on a (n,3) position array -> mat (n,5)
+__device__ __forceinline__ void warp_tile_to_global(const __half *Xs, __half *dst, int64_t row0, int64_t n);
 template <bool WS>
 __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P, int64_t n, const float *__restrict__ position, float *__restrict__ mat,
-                                                               const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2) {
+                                                               const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2,
+                                                               __half *__restrict__ x_save) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half *Wsm = reinterpret_cast<__half *>(smem_raw);
     __half *Xs = Wsm + (64 + 64 + 16) * FIELD_LD + (threadIdx.x >> 5) * 32 * FIELD_LD;
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P,
             for (int k = 0; k < 32; ++k) *reinterpret_cast<__half2 *>(row + 2 * k) = __floats2half2_rn(0.f, 0.f);
         }
         __syncwarp();
+        if (x_save) warp_tile_to_global(Xs, x_save, tile * IRIS_BLOCK + (threadIdx.x & ~31), n);   // encoded inputs, kept for the adjoint
         if (__any_sync(0xffffffffu, active)) {
             float acc[2][8][4];
             warp_gemm<8>(Xs, Wsm, acc);
@@ -365,6 +368,19 @@ __device__ __forceinline__ void warp_tile_to_global(const __half *Xs, __half *ds
     }
 }
 
+// the inverse: rows [row0, row0+32) of a [n][64] global array into the warp's shared tile (rows past n become zeros)
+__device__ __forceinline__ void warp_tile_from_global(__half *Xs, const __half *src, int64_t row0, int64_t n) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int v = it * 32 + lane;
+        const int r = v >> 3, c = (v & 7) * 8;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (row0 + r < n) q = __ldg(reinterpret_cast<const uint4 *>(src + (row0 + r) * 64 + c));
+        *reinterpret_cast<uint4 *>(Xs + r * FIELD_LD + c) = q;
+    }
+}
+
 __device__ __forceinline__ uint32_t relu_mask_bits(const float acc[8][4]) {
     uint32_t m = 0;
 #pragma unroll
@@ -416,7 +432,7 @@ __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
 template <bool WS>
 __global__ void __launch_bounds__(FIELD_BWD_BLOCK, 512 / FIELD_BWD_BLOCK) k_field_backward_dgrad(IrisShadeParams P, int64_t n, const float *__restrict__ position,
                                                                       const float4 *__restrict__ r5, const float *__restrict__ d_mat,
-                                                                      FieldAct act) {
+                                                                      FieldAct act, int x_saved) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half *Wsm = reinterpret_cast<__half *>(smem_raw);              // W1 | W2 | W3 (forward, [out][in])
     __half *W1T = Wsm + (64 + 64 + 16) * FIELD_LD;                     // [in][out] copies for dgrad
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(FIELD_BWD_BLOCK, 512 / FIELD_BWD_BLOCK) k_fiel
             for (int it = 0; it < 8; ++it) {
                 const int v = it * 32 + lane, r = v >> 3, c = (v & 7) * 8;
                 if (row0 + r < n) {
-                    *reinterpret_cast<uint4 *>(act.X + (row0 + r) * 64 + c) = z;
+                    if (!x_saved) *reinterpret_cast<uint4 *>(act.X + (row0 + r) * 64 + c) = z;
                     *reinterpret_cast<uint4 *>(act.h1 + (row0 + r) * 64 + c) = z;
                     *reinterpret_cast<uint4 *>(act.h2 + (row0 + r) * 64 + c) = z;
                     *reinterpret_cast<uint4 *>(act.dh2 + (row0 + r) * 64 + c) = z;
@@ -478,17 +494,23 @@ __global__ void __launch_bounds__(FIELD_BWD_BLOCK, 512 / FIELD_BWD_BLOCK) k_fiel
             }
             continue;
         }
-        const f3 x = mk3(field_coord(p.x, P.field_vmin, P.field_range), field_coord(p.y, P.field_vmin, P.field_range),
-                         field_coord(p.z, P.field_vmin, P.field_range));
-        __half *row = Xs + lane * FIELD_LD;
-        if (active) {
-            field_encode(grid, x, row);
+        if (x_saved) {
+            // act.X already holds the encoded inputs (written by the forward field kernel into the adjoint record)
+            warp_tile_from_global(Xs, act.X, row0, n);
+            __syncwarp();
         } else {
+            const f3 x = mk3(field_coord(p.x, P.field_vmin, P.field_range), field_coord(p.y, P.field_vmin, P.field_range),
+                             field_coord(p.z, P.field_vmin, P.field_range));
+            __half *row = Xs + lane * FIELD_LD;
+            if (active) {
+                field_encode(grid, x, row);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) *reinterpret_cast<__half2 *>(row + 2 * k) = __floats2half2_rn(0.f, 0.f);
+                for (int k = 0; k < 32; ++k) *reinterpret_cast<__half2 *>(row + 2 * k) = __floats2half2_rn(0.f, 0.f);
+            }
+            __syncwarp();
+            warp_tile_to_global(Xs, act.X, row0, n);
         }
-        __syncwarp();
-        warp_tile_to_global(Xs, act.X, row0, n);
         // ---- forward, keeping the ReLU masks
         float acc[2][8][4];
         uint32_t m1[2], m2[2];
@@ -673,18 +695,41 @@ __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams 
                     for (int c = 0; c < 8; ++c) {
                         sx[c] = mine ? wc[c] * gx : 0.f;
                         sy[c] = mine ? wc[c] * gy : 0.f;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            sx[c] += __shfl_xor_sync(0xffffffffu, sx[c], o);
-                            sy[c] += __shfl_xor_sync(0xffffffffu, sy[c], o);
-                        }
                     }
-                    // lane src+c (mod 32) issues corner c: indices come from the group's leader
+                    // Reduce the 8 corner pairs over the warp by recursive halving: at offsets 16, 8, 4 a lane keeps half of its
+                    // items and hands the other half to its partner (8 + 4 + 2 shuffles), then two butterfly steps on the one
+                    // item left: 18 shuffles instead of 80.  Lanes 4c .. 4c+3 end up with the warp sum of corner c.
+                    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u;
+                    float ax[4], ay[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t id = __shfl_sync(0xffffffffu, idxc[c], src);
-                        if (lane == (unsigned)c) red_add_v2(d_grid + 2 * (int64_t)(L.offset + id), sx[c], sy[c]);
+                    for (int k = 0; k < 4; ++k) {
+                        const float keepx = b4 ? sx[k + 4] : sx[k], keepy = b4 ? sy[k + 4] : sy[k];
+                        const float sendx = b4 ? sx[k] : sx[k + 4], sendy = b4 ? sy[k] : sy[k + 4];
+                        ax[k] = keepx + __shfl_xor_sync(0xffffffffu, sendx, 16);
+                        ay[k] = keepy + __shfl_xor_sync(0xffffffffu, sendy, 16);
                     }
+                    float bx[2], by[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const float keepx = b3 ? ax[k + 2] : ax[k], keepy = b3 ? ay[k + 2] : ay[k];
+                        const float sendx = b3 ? ax[k] : ax[k + 2], sendy = b3 ? ay[k] : ay[k + 2];
+                        bx[k] = keepx + __shfl_xor_sync(0xffffffffu, sendx, 8);
+                        by[k] = keepy + __shfl_xor_sync(0xffffffffu, sendy, 8);
+                    }
+                    float rx = (b2 ? bx[1] : bx[0]) + __shfl_xor_sync(0xffffffffu, b2 ? bx[0] : bx[1], 4);
+                    float ry = (b2 ? by[1] : by[0]) + __shfl_xor_sync(0xffffffffu, b2 ? by[0] : by[1], 4);
+                    rx += __shfl_xor_sync(0xffffffffu, rx, 2);
+                    ry += __shfl_xor_sync(0xffffffffu, ry, 2);
+                    rx += __shfl_xor_sync(0xffffffffu, rx, 1);
+                    ry += __shfl_xor_sync(0xffffffffu, ry, 1);
+                    // corner c = lane >> 2 with the group leader's index for it (static select tree, no dynamic register indexing)
+                    uint32_t id8[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) id8[c] = __shfl_sync(0xffffffffu, idxc[c], src);
+                    const uint32_t i4a = b4 ? id8[4] : id8[0], i4b = b4 ? id8[5] : id8[1], i4c = b4 ? id8[6] : id8[2], i4d = b4 ? id8[7] : id8[3];
+                    const uint32_t i2a = b3 ? i4c : i4a, i2b = b3 ? i4d : i4b;
+                    const uint32_t id = b2 ? i2b : i2a;
+                    if ((lane & 3u) == 0u) red_add_v2(d_grid + 2 * (int64_t)(L.offset + id), rx, ry);
                 }
             } else if (has) {
 #pragma unroll

@@ -61,7 +61,8 @@ __device__ int g_tc5_debug = 0;   // 0 normal, 1 skip the encode, 2 skip the MLP
 
 template <bool WS>
 __global__ void __launch_bounds__(TC5_ROWS) k_field_forward_tc5(IrisShadeParams P, int64_t n, const float *__restrict__ position, float *__restrict__ mat,
-                                                                 const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2) {
+                                                                 const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2,
+                                                                 __half *__restrict__ x_save) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sA = smem_raw;
     unsigned char *sW1 = sA + TC5_A_BYTES, *sW2 = sW1 + 8192, *sW3 = sW2 + 8192;
@@ -131,6 +132,17 @@ __global__ void __launch_bounds__(TC5_ROWS) k_field_forward_tc5(IrisShadeParams 
                 for (int k = 0; k < 4; ++k)                                     // K = 64 = 4 x 16: two K chunks per instruction
                     umma_f16(tmem, umma_desc(aA + 2 * k * TC5_A_LBO, TC5_A_LBO, TC5_SBO), umma_desc(aW + 2 * k * wl, wl, TC5_SBO), id, k > 0 ? 1u : 0u);
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            if (layer == 0 && x_save) {
+                // keep the encoded inputs for the adjoint (row-major [n][64] fp16), while the tensor core reads the same tile:
+                // lane v of a warp copies 16-byte chunk v & 7 of row v >> 3, so every store instruction covers 4 full rows
+                const int wrow = tid & ~31, lane = tid & 31;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int v = it * 32 + lane, r = wrow + (v >> 3), c = v & 7;
+                    const int64_t grow = tile * TC5_ROWS + r;
+                    if (grow < n) *reinterpret_cast<uint4 *>(x_save + grow * 64 + c * 8) = *reinterpret_cast<const uint4 *>(sA + c * TC5_A_LBO + r * 16);
+                }
             }
             mbar_wait(bar, phase);
             phase ^= 1u;

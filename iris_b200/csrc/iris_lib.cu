@@ -397,7 +397,8 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
     return IRIS_OK;
 }
 
-static int launch_field(const IrisShadeParams *P, int64_t n, const float *position, float *mat, const float4 *w0, float4 *w1, float4 *w2, cudaStream_t st) {
+static int launch_field(const IrisShadeParams *P, int64_t n, const float *position, float *mat, const float4 *w0, float4 *w1, float4 *w2, cudaStream_t st,
+                        __half *x_save = nullptr) {
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
@@ -418,11 +419,11 @@ static int launch_field(const IrisShadeParams *P, int64_t n, const float *positi
     ProfScope ps(K_FIELD_FORWARD, st);
     if (g_field_impl == 1) {
         const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * g_tc5_ctas);
-        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
-        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
+        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
     } else {
-        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
-        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2);
+        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
+        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
     }
     LAUNCHED();
     return IRIS_OK;
@@ -442,7 +443,7 @@ int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t 
 
 #define FIELD_BWD_CHUNK (1ll << 20)
 static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *position, const float4 *r5, const float *d_mat, float *d_params,
-                              void *workspace, int64_t workspace_bytes, cudaStream_t st) {
+                              void *workspace, int64_t workspace_bytes, cudaStream_t st, __half *x_saved = nullptr) {
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
@@ -455,12 +456,13 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t m = std::min<int64_t>(chunk, n - c0);
         FieldAct act = field_act_carve(workspace, m);
+        if (x_saved) act.X = x_saved + 64 * c0;        // encoded inputs kept by the forward pass: not recomputed, not copied
         const int64_t tiles = (m + FIELD_BWD_BLOCK - 1) / FIELD_BWD_BLOCK;
         const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * (512 / FIELD_BWD_BLOCK));
         {
             ProfScope ps(K_FIELD_BACKWARD, st);
-            if (r5) k_field_backward_dgrad<true><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act);
-            else k_field_backward_dgrad<false><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act);
+            if (r5) k_field_backward_dgrad<true><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act, x_saved ? 1 : 0);
+            else k_field_backward_dgrad<false><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act, x_saved ? 1 : 0);
         }
         LAUNCHED();
         {
@@ -513,7 +515,8 @@ int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {
     const int64_t bwd = ((5 * 4 * n + 15) / 16) * 16 + iris_field_backward_workspace_bytes(n);   // d_mat | activation streams of one chunk
     return std::max(fwd, bwd);
 }
-int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp) { return 6 * 16 * n_pixels * (int64_t)spp; }
+// per sample: 6 float4 of estimator record + the 64 fp16 encoded field inputs (read back by the field adjoint instead of re-gathering)
+int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp) { return (6 * 16 + 128) * n_pixels * (int64_t)spp; }
 
 int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const float *rays, int64_t n_pixels, int32_t spp, const IrisSampler *sampler,
                         float *L, void *record, void *workspace, int64_t workspace_bytes, void *stream) {
@@ -535,7 +538,7 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         k_primary<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1);
     }
     LAUNCHED();
-    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st);
+    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st, record ? reinterpret_cast<__half *>(reinterpret_cast<float4 *>(record) + 6 * n) : nullptr);
     if (rc) return rc;
     if (g_single_impl == 0) {
         ProfScope ps(K_BOUNCE_SINGLE, st);
@@ -603,8 +606,9 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
     LAUNCHED();
     if (d_params) {
         const int64_t off = ((5 * 4 * n + 15) / 16) * 16;
+        __half *x_saved = reinterpret_cast<__half *>(const_cast<float4 *>(reinterpret_cast<const float4 *>(record)) + 6 * n);
         return run_field_backward(P, n, nullptr, reinterpret_cast<const float4 *>(record) + 5 * n, d_mat, d_params,
-                                  reinterpret_cast<unsigned char *>(workspace) + off, workspace_bytes - off, st);
+                                  reinterpret_cast<unsigned char *>(workspace) + off, workspace_bytes - off, st, x_saved);
     }
     return IRIS_OK;
 }
