@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(FIELD_BWD_BLOCK, 512 / FIELD_BWD_BLOCK) k_fiel
 // one lane per corner issues the reduction -- "reduce per warp, then one atomic per parameter tile" -- which removes the
 // same-address serialisation at the L2 atomic units.  Lanes in many different cells (fine levels) go straight to the reductions.
 #ifndef FIELD_SCATTER_MAX_GROUPS
-#define FIELD_SCATTER_MAX_GROUPS 4
+#define FIELD_SCATTER_MAX_GROUPS 8
 #endif
 template <bool WS>
 __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams P, int64_t n, const float *__restrict__ position,

@@ -42,8 +42,8 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
-enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_SINGLE_GEN, K_TRACE_QUEUE, K_SINGLE_SHADE, K_COUNT };
-static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish", "k_single_gen", "k_trace_queue", "k_single_shade"};
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_SINGLE_GEN, K_TRACE_QUEUE, K_SINGLE_SHADE, K_BAKE_GEN, K_BAKE_SHADE, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish", "k_single_gen", "k_trace_queue", "k_single_shade", "k_bake_gen", "k_bake_shade"};
 struct ProfSpan { int id; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
@@ -75,6 +75,7 @@ static int g_sm_count = 0;
 static int g_tc5_ctas = 4;      // tcgen05 kernel: CTAs per SM (34.9 KB smem, 64 TMEM columns each)
 static int g_single_impl = 1;      // 1: wavefront bounce (k_single_gen -> k_trace_queue -> k_single_shade), 0: fused k_bounce_single
 static int64_t g_single_chunk = 8 << 20;   // samples per wavefront chunk
+static int g_bake_impl = 0;        // 0: fused k_bake with block-level direction sort (measured faster: 2.75 vs 2.13 G rays/s on c2), 1: ray queue
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
 static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
 static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
@@ -197,6 +198,7 @@ int64_t iris_launch_count(void) { return g_launches.load(); }
 int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "field_forward_impl") == 0 && (value == 0 || value == 1)) { g_field_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "intersect_impl") == 0 && (value == 0 || value == 1)) { g_intersect_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "bake_impl") == 0 && (value == 0 || value == 1)) { g_bake_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
     if (name && std::strcmp(name, "persist_ctas_per_sm") == 0 && value >= 1 && value <= 16) { g_persist_ctas = value; return IRIS_OK; }
@@ -375,6 +377,17 @@ static int check_params(const IrisShadeParams *P, bool need_field) {
     return IRIS_OK;
 }
 
+// ray queue of one chunk of the wavefront bounce: counters | rays (2 x 2 float4) | hits (2 float4) | state streams
+static const int64_t SINGLE_MAX_CHUNKS = 1024;
+static int64_t single_chunk_samples(int64_t n) {
+    int64_t c = std::min<int64_t>(n, g_single_chunk);
+    while ((n + c - 1) / c > SINGLE_MAX_CHUNKS) c *= 2;
+    return std::max<int64_t>(c, 1);
+}
+static int64_t single_queue_bytes(int64_t n) {
+    return 8 * SINGLE_MAX_CHUNKS + (4 + 2 + IRIS_SINGLE_STATE_STREAMS) * 16 * single_chunk_samples(n);
+}
+
 int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roughness, const float *position, const float *normal, const float *wo,
               int64_t n_pixels, int32_t spp, const IrisSampler *sampler, float *out0, float *out1, void *stream) {
     if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
@@ -389,11 +402,45 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
     CUDA_TRY(cudaMemsetAsync(out0, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     if (mode == 1) CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     const int64_t n = n_pixels * spp;
-    ProfScope ps(mode == 0 ? K_BAKE_DIFFUSE : K_BAKE_SPECULAR, st);
-    const unsigned gb = (unsigned)((n + IRIS_SORT_BLOCK - 1) / IRIS_SORT_BLOCK);
-    if (mode == 0) k_bake<0><<<gb, IRIS_SORT_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
-    else k_bake<1><<<gb, IRIS_SORT_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
-    LAUNCHED();
+    if (g_bake_impl == 0) {
+        ProfScope ps(mode == 0 ? K_BAKE_DIFFUSE : K_BAKE_SPECULAR, st);
+        const unsigned gb = (unsigned)((n + IRIS_SORT_BLOCK - 1) / IRIS_SORT_BLOCK);
+        if (mode == 0) k_bake<0><<<gb, IRIS_SORT_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
+        else k_bake<1><<<gb, IRIS_SORT_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1);
+        LAUNCHED();
+        return IRIS_OK;
+    }
+    // ray-queue form: generate -> persistent trace -> shade, in chunks; the queue is stream-ordered scratch memory
+    const int64_t nc_max = single_chunk_samples(n);
+    const int64_t n_chunks = (n + nc_max - 1) / nc_max;
+    unsigned char *scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync(&scratch, 8 * SINGLE_MAX_CHUNKS + 3 * 16 * (size_t)nc_max, st));
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(scratch);
+    float4 *ro = reinterpret_cast<float4 *>(scratch + 8 * SINGLE_MAX_CHUNKS), *rd = ro + nc_max, *hit = rd + nc_max;
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * (size_t)n_chunks, st));
+    int chunk = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += nc_max, ++chunk) {
+        const int64_t nc = std::min(nc_max, n - i0);
+        {
+            ProfScope ps(K_BAKE_GEN, st);
+            if (mode == 0) k_bake_gen<0><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*sampler, roughness, position, normal, wo, i0, nc, spp, ro, rd);
+            else k_bake_gen<1><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*sampler, roughness, position, normal, wo, i0, nc, spp, ro, rd);
+        }
+        LAUNCHED();
+        {
+            ProfScope ps(K_TRACE_QUEUE, st);
+            const int grid = (int)std::min<int64_t>(blocks_for(nc), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
+            k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, nc, 0, hit, counters + chunk);
+        }
+        LAUNCHED();
+        {
+            ProfScope ps(K_BAKE_SHADE, st);
+            if (mode == 0) k_bake_shade<0><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, roughness, normal, wo, i0, nc, spp, rd, hit, out0, out1);
+            else k_bake_shade<1><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, roughness, normal, wo, i0, nc, spp, rd, hit, out0, out1);
+        }
+        LAUNCHED();
+    }
+    CUDA_TRY(cudaFreeAsync(scratch, st));
     return IRIS_OK;
 }
 
@@ -496,17 +543,6 @@ int iris_field_backward(const IrisShadeParams *P, const float *position, const f
     int rc = ensure_device_setup(dev);
     if (rc) return rc;
     return run_field_backward(P, n, position, nullptr, d_mat, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
-}
-
-// ray queue of one chunk of the wavefront bounce: counters | rays (2 x 2 float4) | hits (2 float4) | state streams
-static const int64_t SINGLE_MAX_CHUNKS = 1024;
-static int64_t single_chunk_samples(int64_t n) {
-    int64_t c = std::min<int64_t>(n, g_single_chunk);
-    while ((n + c - 1) / c > SINGLE_MAX_CHUNKS) c *= 2;
-    return std::max<int64_t>(c, 1);
-}
-static int64_t single_queue_bytes(int64_t n) {
-    return 8 * SINGLE_MAX_CHUNKS + (4 + 2 + IRIS_SINGLE_STATE_STREAMS) * 16 * single_chunk_samples(n);
 }
 
 int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {

@@ -266,6 +266,48 @@ __device__ __forceinline__ Hit queue_hit_surface(const SceneView &S, float4 q, f
     return h;
 }
 
+// bake through the ray queue (bake_shading.py:108-123 / :168-188): sample a direction per lane, trace, weight the radiance found.
+template <int MODE>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_bake_gen(IrisSampler smp, float roughness, const float *__restrict__ position, const float *__restrict__ normal,
+                                                          const float *__restrict__ wo_in, int64_t i0, int64_t nc, int spp, float4 *__restrict__ ro,
+                                                          float4 *__restrict__ rd) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nc) return;
+    const int64_t i = i0 + j, pix = i / spp;
+    const f3 x = ld3(position, pix), nr = ld3(normal, pix);
+    const float4 u = sample4(smp, i, 0);
+    const f3 wi = MODE == 0 ? diffuse_sampler(u.x, u.y, nr) : specular_sampler(u.x, u.y, roughness, ld3(wo_in, pix), nr);
+    ro[j] = make_float4(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
+    rd[j] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_bake_shade(SceneView S, IrisShadeParams P, float roughness, const float *__restrict__ normal,
+                                                            const float *__restrict__ wo_in, int64_t i0, int64_t nc, int spp, const float4 *__restrict__ rd,
+                                                            const float4 *__restrict__ hit, float *out0, float *out1) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = j < nc;
+    const int64_t i = i0 + j, pix = in_range ? i / spp : 0;
+    f3 L0 = mk3(0.f, 0.f, 0.f), L1 = L0;
+    if (in_range) {
+        const float4 dq = rd[j];
+        const f3 wi = mk3(dq.x, dq.y, dq.z);
+        float w0 = 1.f, w1 = 0.f;
+        if (MODE == 1) specular_weights(wi, ld3(wo_in, pix), ld3(normal, pix), roughness, w0, w1);
+        f3 hp, hn;
+        const Hit h = queue_hit_surface(S, hit[j], wi, hp, hn);
+        int32_t e;
+        float epdf;
+        bool vn;
+        const f3 Le = radiance_at_hit(P, h, hp, e, epdf, vn);
+        L0 = Le * w0;
+        L1 = Le * w1;
+    }
+    const float inv = 1.f / (float)spp;
+    pixel_accumulate(out0, pix, in_range, L0, inv);
+    if (MODE == 1) pixel_accumulate(out1, pix, in_range, L1, inv);
+}
+
 // path_tracing_single, generator half: everything of utils/path_tracing.py:359-404 that does not depend on a ray cast.
 // Per-sample state streams (float4, chunk-local index j, stride nc):
 //   s0 = (L_nee.rgb if unoccluded, pdf_b)   s1 = (wb.rgb, e_nee)                      e_nee < 0: no shadow ray

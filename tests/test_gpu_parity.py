@@ -516,6 +516,32 @@ def test_wavefront_bounce_equals_fused_bounce(small):
         core.C.check(lib.iris_set_option(b"single_chunk_log2", 23))
 
 
+def test_bake_queue_equals_fused_bake(small):
+    """bake runs as one fused kernel with a block-level direction sort by default; the ray-queue form (generate -> persistent
+    trace -> shade) is kept behind a switch.  Same rays, same arithmetic: equal up to the order of the per-pixel float atomics."""
+    from iris_b200 import core
+    lib = core.C.lib()
+    dev, spp = small["dev"], small["spp"]
+    r = torch.as_tensor(small["rays"])
+    pos, nrm, _, _, _ = small["osc"].ray_intersect(r[:, 0:3], r[:, 3:6])
+    pos, nrm, wo = pos.to(dev), nrm.to(dev), (-r[:, 3:6]).to(dev)
+    smp = core.Sampler(seed=5)
+    try:
+        outs = []
+        for impl, log2 in ((0, 23), (1, 23), (1, 10)):
+            core.C.check(lib.iris_set_option(b"bake_impl", impl))
+            core.C.check(lib.iris_set_option(b"single_chunk_log2", log2))
+            d = core.bake(small["scene"], small["tables"], 0, 1.0, pos, nrm, None, spp, smp)
+            s0, s1 = core.bake(small["scene"], small["tables"], 1, 0.3, pos, nrm, wo, spp, smp)
+            outs.append((d, s0, s1))
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    finally:
+        core.C.check(lib.iris_set_option(b"bake_impl", 0))
+        core.C.check(lib.iris_set_option(b"single_chunk_log2", 23))
+
+
 def test_persistent_intersect_equals_static_intersect():
     """ray_intersect with dynamic ray fetch (intersect_impl = 1) returns bit-identical hits."""
     dev = _gpu()
