@@ -41,6 +41,8 @@ WORKLOADS = {
                desc="scaling sweep: 5M-tri room, 64 views 1920x1440 in total (sharded over the GPUs), spp=128, path_tracing_single fwd+bwd, field + emitter gradients"),
     "c2": dict(tris=1_000_000, emitters=16, views=1, width=640, height=480, SPP=64, spp=64, brdf_grad=False, bake=True,
                desc="shading-map bake (bake_shading.py): 1M-tri room, 640x480, spp=64, diffuse map + 6 roughness levels x 2 Fresnel maps, forward only"),
+    "brdf": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=1, spp=1, brdf_grad=True, maps=True,
+                 desc="train_brdf_crf step (SURVEY 8f-2): NGPBRDF field at the primary hits of 8 views 1280x960 -> kd/ks shading from baked maps (6 roughness levels) -> EmorCRF -> MSE + diffuse regulariser, backward to field params and CRF weight"),
     "c1": dict(tris=10_000, emitters=2, views=1, width=64, height=64, SPP=16, spp=16, brdf_grad=True,
                desc="Cornell ~10k tris, 64x64, spp=16, path_tracing_single fwd+bwd (reference's CPU-runnable case)"),
 }
@@ -212,6 +214,76 @@ def bench_bake(a, w, sc, scene, tables, dev, config, stats):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ train_brdf_crf step (8f-2)
+def bench_brdf(a, w, sc, scene, dev, config, stats):
+    """One step = the shading block of train_brdf_crf.py:176-211 over every valid pixel of the views: ray_intersect, field forward,
+    kd/ks shading from the baked maps, EmorCRF, MSE + loss_d, and the adjoint down to mlp.params and the CRF weight."""
+    import torch
+    from iris_b200 import core, ops
+    from iris_b200.crf import EmorCRF
+    lib = core.C.lib()
+    g = torch.Generator().manual_seed(0)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mlp = torch.nn.Module()
+            self.mlp.params = torch.nn.Parameter(bench_params().to(dev))
+            self.voxel_min, self.voxel_max = sc.voxel_bounds()
+    net = Net()
+    x = np.linspace(0.0, 1.0, 1024, dtype=np.float32)
+    crf = EmorCRF(dim=11, tables=(x ** (1 / 2.2), np.stack([np.sin((k + 1) * np.pi * x) * 0.05 for k in range(11)]).astype(np.float32))).to(dev)
+    views = []
+    for v in range(w["views"]):
+        rays = torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=v + 1)).to(dev)
+        n = rays.shape[0]
+        views.append(dict(o=rays[:, 0:3].contiguous(), d=rays[:, 3:6].contiguous(), diffuse=torch.rand(n, 3, generator=g).to(dev),
+                          spec0=torch.rand(n, 6, 3, generator=g).to(dev), spec1=(torch.rand(n, 6, 3, generator=g) * 0.2).to(dev),
+                          rgb=torch.rand(n, 3, generator=g).to(dev)))
+    exposure = torch.ones(1, device=dev)
+
+    def step():
+        net.mlp.params.grad = None
+        crf.weight.grad = None
+        n_valid, total = 0, 0.0
+        for V in views:
+            t, prim, uv, p, nrm = scene.intersect_raw(V["o"], V["d"])
+            valid = prim >= 0
+            L, mat = ops.brdf_shading(net, p[valid], V["diffuse"][valid], V["spec0"][valid], V["spec1"][valid])
+            ldr = crf(L, exposure)
+            loss = torch.nn.functional.mse_loss(ldr, V["rgb"][valid]) + 5e-4 * ((mat["roughness"] - 1).abs().mean() + mat["metallic"].mean())
+            loss.backward()
+            n_valid += int(L.shape[0])
+            total += float(loss.detach())
+        return n_valid, total
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.iris_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        n_valid, loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = n_valid * a.steps / (ms * 1e-3)
+    peak = 6518.6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    bpp = ray_bytes(sc.n_tris) + 2048 + 176 + 12 + 24 + 20      # primary cast + field fwd+bwd gathers/scatters (SURVEY 8d) + maps + L + rgb + mat
+    line = dict(metric="brdf_crf_step_pixels_per_sec", value=value, unit="pixels/s", n_gpus=1, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms / a.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config, gpu_launches=int(lib.iris_launch_count() - l0),
+                roofline=dict(bound="hbm", kernel="step", achieved=value * bpp / 1e9, peak=peak, unit="GB/s", frac=value * bpp / 1e9 / peak, traffic=None,
+                              algorithmic_bytes_per_pixel=bpp),
+                scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
+                loss=loss, d_params_abs_sum=float(net.mlp.params.grad.abs().sum()), d_crf_weight_abs_sum=float(crf.weight.grad.abs().sum()))
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     a = parse()
@@ -261,6 +333,8 @@ def main():
     tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(256), bench_params(), sc.voxel_bounds())
     if w.get("bake"):
         return bench_bake(a, w, sc, scene, tables, dev, config, stats)
+    if w.get("maps"):
+        return bench_brdf(a, w, sc, scene, dev, config, stats)
     if w.get("strong"):                                   # fixed total work, views sharded over the ranks
         lo_v, hi_v = idist.shard_range(w["views"], rank, world)
         views = [v + 1 for v in range(lo_v, hi_v)]

@@ -180,6 +180,20 @@ int iris_trace_indirect(const IrisScene *scene, const IrisShadeParams *params, c
                         void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training-step shading from baked maps -- train_brdf_crf.py:193-206 with utils/ops.py:99-119 (lerp_specular):
+ *   kd = albedo (1 - metallic), ks = 0.04 (1 - metallic) + albedo metallic,
+ *   L = kd * diffuse + ks * lerp(specular0, roughness) + lerp(specular1, roughness)
+ * mat (n,5) = (albedo rgb, roughness, metallic) as iris_field_forward writes it; diffuse (n,3); specular0/1 (n,n_levels,3), the
+ * maps baked by iris_bake at roughness levels linspace(0.02, 1, n_levels).  Backward: d_mat (n,5) += J^T dL (zero it, or pre-load
+ * it with the gradients of the regularisers that act on albedo / roughness / metallic directly, train_brdf_crf.py:213-302); feed
+ * d_mat to iris_field_backward.  The maps are data: no gradient.
+ * ---------------------------------------------------------------------------------------------- */
+int iris_brdf_shading_forward(const float *mat, const float *diffuse, const float *specular0, const float *specular1, int32_t n_levels,
+                              int64_t n, float *L, void *stream);
+int iris_brdf_shading_backward(const float *mat, const float *diffuse, const float *specular0, const float *specular1, int32_t n_levels,
+                               int64_t n, const float *dL, float *d_mat, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * EmorCRF -- the camera response applied right after the estimator in every trainer (crf/model_crf.py:68-86,
  * train_emitter.py:191-193): ldr = lerp(crf_c, clip(hdr * exposure, 0, 1)) with crf (3, n_bins) = f0 + weight @ basis sampled on a
  * regular grid over [0,1].  exposure: (n) with exposure_stride 1, or one value with stride 0.  Backward: d_hdr (n,3) written,

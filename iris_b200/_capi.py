@@ -56,6 +56,8 @@ PROTOTYPES = {
     "iris_path_tracing_det": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32,
                                              ctypes.POINTER(IrisSampler), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_trace_indirect": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(IrisSampler), c_vp, c_vp, c_i64, c_vp]),
+    "iris_brdf_shading_forward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
+    "iris_brdf_shading_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
     "iris_crf_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "iris_crf_backward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "iris_launch_count": (c_i64, []),

@@ -227,6 +227,32 @@ def field_backward(tables, position, d_mat, d_params=None, workspace=None):
     return d_params
 
 
+def brdf_shading_forward(mat, diffuse, specular0, specular1):
+    """train_brdf_crf.py:193-206: L = kd*diffuse + ks*lerp_specular(specular0, r) + lerp_specular(specular1, r).  mat (n,5)."""
+    mat, diffuse = mat.contiguous().float(), diffuse.contiguous().float()
+    specular0, specular1 = specular0.contiguous().float(), specular1.contiguous().float()
+    n, R = mat.shape[0], specular0.shape[-2]
+    if diffuse.shape != (n, 3) or specular0.shape != (n, R, 3) or specular1.shape != (n, R, 3):
+        raise ValueError("brdf_shading: expected mat (n,5), diffuse (n,3), specular0/1 (n,R,3)")
+    L = torch.empty(n, 3, device=mat.device)
+    with torch.cuda.device(mat.device):
+        C.check(C.lib().iris_brdf_shading_forward(C.ptr(mat), C.ptr(diffuse), C.ptr(specular0), C.ptr(specular1), R, n, C.ptr(L), C.stream_ptr()))
+    return L
+
+
+def brdf_shading_backward(mat, diffuse, specular0, specular1, dL, d_mat=None):
+    """d_mat (n,5) += J^T dL; returns d_mat (zeros are allocated when none is passed)."""
+    mat, diffuse, dL = mat.contiguous().float(), diffuse.contiguous().float(), dL.contiguous().float()
+    specular0, specular1 = specular0.contiguous().float(), specular1.contiguous().float()
+    n, R = mat.shape[0], specular0.shape[-2]
+    if d_mat is None:
+        d_mat = torch.zeros(n, 5, device=mat.device)
+    with torch.cuda.device(mat.device):
+        C.check(C.lib().iris_brdf_shading_backward(C.ptr(mat), C.ptr(diffuse), C.ptr(specular0), C.ptr(specular1), R, n, C.ptr(dL), C.ptr(d_mat),
+                                                   C.stream_ptr()))
+    return d_mat
+
+
 def single_forward(scene, tables, rays, spp, sampler, want_record=False, workspace=None):
     """path_tracing_single forward.  Returns (L (B,3), record or None)."""
     rays = rays.contiguous().float()

@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "wavefront.cuh"
 #include "crf.cuh"
+#include "shade_maps.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -787,6 +788,26 @@ int iris_trace_indirect(const IrisScene *s, const IrisShadeParams *P, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ EmorCRF
+int iris_brdf_shading_forward(const float *mat, const float *diffuse, const float *specular0, const float *specular1, int32_t n_levels, int64_t n,
+                              float *L, void *stream) {
+    if (n < 0 || n_levels < 2) return fail(IRIS_ERR_INVALID, "bad brdf_shading arguments");
+    if (n == 0) return IRIS_OK;
+    if (!mat || !diffuse || !specular0 || !specular1 || !L) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_brdf_shading_forward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mat, diffuse, specular0, specular1, n_levels, n, L);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_brdf_shading_backward(const float *mat, const float *diffuse, const float *specular0, const float *specular1, int32_t n_levels, int64_t n,
+                               const float *dL, float *d_mat, void *stream) {
+    if (n < 0 || n_levels < 2) return fail(IRIS_ERR_INVALID, "bad brdf_shading arguments");
+    if (n == 0) return IRIS_OK;
+    if (!mat || !diffuse || !specular0 || !specular1 || !dL || !d_mat) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_brdf_shading_backward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mat, diffuse, specular0, specular1, n_levels, n, dL, d_mat);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
 int iris_crf_forward(const float *hdr, const float *exposure, int32_t exposure_stride, const float *crf, int32_t n_bins, int64_t n, float *ldr,
                      void *stream) {
     if (n < 0 || n_bins < 2 || (exposure_stride != 0 && exposure_stride != 1)) return fail(IRIS_ERR_INVALID, "bad crf arguments");

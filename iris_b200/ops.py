@@ -190,7 +190,15 @@ class FieldForward(torch.autograd.Function):
 
 def field(material_net, position):
     """NGPBRDF.forward (model/brdf.py:243-260): dict(albedo (N,3), roughness (N,1), metallic (N,1))."""
-    dev = position.device
+    T = _field_tables(material_net, position.device)
+    p = material_net.mlp.params
+    shape = position.shape[:-1]
+    mat = FieldForward.apply(p, T, position.reshape(-1, 3).float().contiguous())
+    return {"albedo": mat[:, 0:3].reshape(*shape, 3), "roughness": mat[:, 3:4].reshape(*shape, 1), "metallic": mat[:, 4:5].reshape(*shape, 1)}
+
+
+# ------------------------------------------------------------------------------------------------ training-step shading (train_brdf_crf.py)
+def _field_tables(material_net, dev):
     cache = material_net.__dict__.setdefault("_iris_cache", {})
     T = cache.get("tables")
     p = material_net.mlp.params
@@ -198,6 +206,59 @@ def field(material_net, position):
     if T is None or T.device != dev or cache.get("field_key") != key:
         T = core.ShadingTables(dev).set_field(p, material_net.voxel_min, material_net.voxel_max)
         cache["tables"], cache["field_key"] = T, key
-    shape = position.shape[:-1]
-    mat = FieldForward.apply(p, T, position.reshape(-1, 3).float().contiguous())
-    return {"albedo": mat[:, 0:3].reshape(*shape, 3), "roughness": mat[:, 3:4].reshape(*shape, 1), "metallic": mat[:, 4:5].reshape(*shape, 1)}
+    return T
+
+
+class BrdfShading(torch.autograd.Function):
+    """field forward -> shading from the baked maps, and their adjoints, as ONE autograd node: the (n,5) material tensor is
+    returned as well, so regularisers written in torch on albedo / roughness / metallic add their gradient to the same d_mat
+    before the single field adjoint runs."""
+
+    @staticmethod
+    def forward(ctx, params, tables, position, diffuse, specular0, specular1):
+        mat = core.field_forward(tables, position)
+        L = core.brdf_shading_forward(mat, diffuse, specular0, specular1)
+        ctx.tables = tables
+        ctx.n_params = params.numel()
+        ctx.save_for_backward(position, mat, diffuse, specular0, specular1)
+        return L, mat
+
+    @staticmethod
+    def backward(ctx, dL, d_mat_up):
+        position, mat, diffuse, specular0, specular1 = ctx.saved_tensors
+        d_mat = d_mat_up.contiguous().float().clone() if d_mat_up is not None else None
+        d_mat = core.brdf_shading_backward(mat, diffuse, specular0, specular1, dL, d_mat)
+        d = torch.zeros(ctx.n_params, device=dL.device, dtype=torch.float32)
+        core.field_backward(ctx.tables, position, d_mat, d)
+        return d, None, None, None, None, None
+
+
+def brdf_shading(material_net, positions, diffuse, specular0, specular1):
+    """The shading block of train_brdf_crf.py:193-206 fused with NGPBRDF.forward.  Returns (L (n,3), mat dict) where the dict has the
+    reference's keys (albedo (n,3), roughness (n,1), metallic (n,1)), all differentiable w.r.t. material_net.mlp.params."""
+    position = positions.reshape(-1, 3).float().contiguous()
+    T = _field_tables(material_net, position.device)
+    L, mat = BrdfShading.apply(material_net.mlp.params, T, position, diffuse, specular0, specular1)
+    return L, {"albedo": mat[:, 0:3], "roughness": mat[:, 3:4], "metallic": mat[:, 4:5]}
+
+
+class _LerpSpecular(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, specular, roughness):
+        n = specular.shape[0]
+        mat = torch.ones(n, 5, device=specular.device)              # albedo = metallic = 1  ->  kd = 0, ks = 1
+        mat[:, 3] = roughness.reshape(-1)
+        zero3, zeroS = torch.zeros(n, 3, device=specular.device), torch.zeros_like(specular)
+        ctx.save_for_backward(mat, zero3, specular, zeroS)
+        return core.brdf_shading_forward(mat, zero3, specular, zeroS)
+
+    @staticmethod
+    def backward(ctx, dL):
+        mat, zero3, specular, zeroS = ctx.saved_tensors
+        d_mat = core.brdf_shading_backward(mat, zero3, specular, zeroS, dL)
+        return None, d_mat[:, 3:4]
+
+
+def lerp_specular(specular, roughness):
+    """utils/ops.py:99-119 on the CUDA kernel (gradient to roughness; the baked maps are data)."""
+    return _LerpSpecular.apply(specular.float().contiguous(), roughness.float())

@@ -52,3 +52,20 @@ def grid_fingerprint(g):
     top = np.argsort(-np.abs(g))[:4096]
     top.sort()
     return np.array(lv_sum), np.array(lv_abs), top.astype(np.int64), g[top].astype(np.float32)
+
+
+def shading_inputs(n=4096, R=6, seed=21):
+    """Seeded inputs of the training-step shading case (also used by the tests): material in the ranges NGPBRDF produces,
+    roughness rows 0..2R-1 pinned to the interval ends and the baked levels themselves."""
+    g = torch.Generator().manual_seed(seed)
+    albedo = torch.rand(n, 3, generator=g)
+    roughness = torch.rand(n, 1, generator=g) * 0.98 + 0.02
+    metallic = torch.rand(n, 1, generator=g)
+    levels = torch.linspace(0.02, 1.0, R)
+    roughness[:R, 0] = levels
+    roughness[R:2 * R, 0] = (levels + 1e-4).clamp(max=1.0)
+    diffuse = torch.rand(n, 3, generator=g) * 2.0
+    specular0 = torch.rand(n, R, 3, generator=g) * 3.0
+    specular1 = torch.rand(n, R, 3, generator=g) * 0.5
+    dL = torch.randn(n, 3, generator=g)
+    return dict(albedo=albedo, roughness=roughness, metallic=metallic, diffuse=diffuse, specular0=specular0, specular1=specular1, dL=dL)

@@ -35,7 +35,30 @@ def single_with_grads(c, osc):
                 d_mlp=gp[:9216], d_grid_level_sum=lv_sum, d_grid_level_abs=lv_abs, d_grid_top_idx=top_i, d_grid_top_val=top_v)
 
 
+def shading_golden():
+    """tests/golden/shading.npz: the reference's own lerp_specular (utils/ops.py:99-119, imported from /root/reference) inside the
+    six restated lines of train_brdf_crf.py:197-206, forward and autograd gradients."""
+    import importlib.util
+    from oracle import shading as OS
+    spec = importlib.util.spec_from_file_location("_ref_utils_ops", "/root/reference/utils/ops.py")
+    ref_ops = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(ref_ops)
+    x = cases.shading_inputs()
+    a, r, m = (x[k].clone().requires_grad_(True) for k in ("albedo", "roughness", "metallic"))
+    L = OS.brdf_shading(a, r, m, x["diffuse"], x["specular0"], x["specular1"], lerp=ref_ops.lerp_specular)
+    L.backward(x["dL"])
+    with torch.no_grad():
+        assert torch.equal(ref_ops.lerp_specular(x["specular0"], x["roughness"]), OS.lerp_specular(x["specular0"], x["roughness"]))
+    g = dict(L=L.detach().numpy(), d_albedo=a.grad.numpy(), d_roughness=r.grad.numpy(), d_metallic=m.grad.numpy(),
+             lerp0=ref_ops.lerp_specular(x["specular0"], x["roughness"]).numpy())
+    np.savez_compressed(os.path.join(HERE, "shading.npz"), **g)
+    print("shading.npz", {k: v.shape for k, v in g.items()})
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "shading":
+        return shading_golden()
     out = {}
     # ---------------- small: every estimator
     c = cases.build("small")
@@ -71,6 +94,7 @@ def main():
     g = single_with_grads(c, osc)
     np.savez_compressed(os.path.join(HERE, "c1.npz"), **g)
     print("c1.npz", {k: v.shape for k, v in g.items()})
+    shading_golden()
 
 
 if __name__ == "__main__":

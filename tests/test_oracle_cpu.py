@@ -149,3 +149,20 @@ def test_brdf_gradient_finite_differences():
         e[k] = h
         fd = ((f(x.detach() + e) - f(x.detach() - e)) * w).sum(-1) / (2 * h)
         assert torch.allclose(fd, x.grad[:, k], rtol=1e-5, atol=1e-7)
+
+
+def test_shading_oracle_matches_reference_golden():
+    """oracle/shading.py (train_brdf_crf.py:197-206 + utils/ops.py:99-119) against tests/golden/shading.npz, which was produced with the
+    reference's own lerp_specular."""
+    import torch
+    from oracle import shading as OS
+    from tests.golden import cases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "shading.npz"))
+    x = cases.shading_inputs()
+    a, r, m = (x[k].clone().requires_grad_(True) for k in ("albedo", "roughness", "metallic"))
+    L = OS.brdf_shading(a, r, m, x["diffuse"], x["specular0"], x["specular1"])
+    L.backward(x["dL"])
+    assert np.array_equal(L.detach().numpy(), g["L"])
+    assert np.array_equal(a.grad.numpy(), g["d_albedo"]) and np.array_equal(r.grad.numpy(), g["d_roughness"]) and np.array_equal(m.grad.numpy(), g["d_metallic"])
+    with torch.no_grad():
+        assert np.array_equal(OS.lerp_specular(x["specular0"], x["roughness"]).numpy(), g["lerp0"])
