@@ -180,6 +180,27 @@ int iris_trace_indirect(const IrisScene *scene, const IrisShadeParams *params, c
                         void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Voxel surface-light-field bake on the device -- slf_bake.py:70-145 with model/slf.py:16-61 (the stage that produces the vslf.npz
+ * the estimators read).  All arrays are device arrays; `valid` (n bytes, may be NULL = all valid) is ray_intersect's mask.
+ *   iris_slf_bounds      running min / max over every coordinate of the valid points (slf_bake.py:73-85).  state: 16 bytes,
+ *                        [0],[1] = min, max as floats (valid after every call), [2],[3] internal; reset != 0 on the first call.
+ *   iris_slf_mark        occupancy[cell] = 1 for the voxel of every valid point (SpatialHist > 0, :96-113); zero it first.
+ *                        cell = ((gz * H) + gy) * H + gx, g = clamp(trunc((x - voxel_min) / voxel_range * H), 0, H-1).
+ *   iris_slf_index       inds (H^3 int32) = -1 for empty voxels, else the rank among the occupied ones in raster order -- the order of
+ *                        torch.where(mask) (model/slf.py:29-32); n_cells (host) = number of occupied voxels.  Synchronises the stream.
+ *   iris_slf_accumulate  sum[inds[cell]] += radiance, count[inds[cell]] += 1 (VoxelSLF.scatter_add, model/slf.py:56-61).
+ *   iris_slf_finalize    sum /= max(count, 1) in place (slf_bake.py:138): sum becomes the `radiance` table of IrisShadeParams.
+ * ---------------------------------------------------------------------------------------------- */
+int iris_slf_bounds(const float *positions, const uint8_t *valid, int64_t n, int32_t reset, float *state, void *stream);
+int iris_slf_mark(const float *positions, const uint8_t *valid, int64_t n, float voxel_min, float voxel_range, int32_t H, int32_t *occupancy,
+                  void *stream);
+int64_t iris_slf_index_workspace_bytes(int32_t H);
+int iris_slf_index(const int32_t *occupancy, int32_t H, int32_t *inds, int64_t *n_cells, void *workspace, int64_t workspace_bytes, void *stream);
+int iris_slf_accumulate(const float *positions, const uint8_t *valid, const float *radiance, int64_t n, float voxel_min, float voxel_range,
+                        int32_t H, const int32_t *inds, float *sum, int32_t *count, void *stream);
+int iris_slf_finalize(float *sum, const int32_t *count, int64_t n_cells, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training-step shading from baked maps -- train_brdf_crf.py:193-206 with utils/ops.py:99-119 (lerp_specular):
  *   kd = albedo (1 - metallic), ks = 0.04 (1 - metallic) + albedo metallic,
  *   L = kd * diffuse + ks * lerp(specular0, roughness) + lerp(specular1, roughness)

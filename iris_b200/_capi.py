@@ -56,6 +56,12 @@ PROTOTYPES = {
     "iris_path_tracing_det": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32,
                                              ctypes.POINTER(IrisSampler), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_trace_indirect": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(IrisSampler), c_vp, c_vp, c_i64, c_vp]),
+    "iris_slf_bounds": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "iris_slf_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float, c_i32, c_vp, c_vp]),
+    "iris_slf_index_workspace_bytes": (c_i64, [c_i32]),
+    "iris_slf_index": (ctypes.c_int, [c_vp, c_i32, c_vp, ctypes.POINTER(c_i64), c_vp, c_i64, c_vp]),
+    "iris_slf_accumulate": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "iris_slf_finalize": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "iris_brdf_shading_forward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "iris_brdf_shading_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
     "iris_crf_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp]),

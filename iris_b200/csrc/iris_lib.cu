@@ -15,6 +15,7 @@
 #include "wavefront.cuh"
 #include "crf.cuh"
 #include "shade_maps.cuh"
+#include "slf_bake.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -788,6 +789,92 @@ int iris_trace_indirect(const IrisScene *s, const IrisShadeParams *P, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ EmorCRF
+// ------------------------------------------------------------------------------------------------ SLF bake (slf_bake.py, model/slf.py)
+int iris_slf_bounds(const float *positions, const uint8_t *valid, int64_t n, int32_t reset, float *state, void *stream) {
+    if (n < 0 || !state) return fail(IRIS_ERR_INVALID, "bad slf_bounds arguments");
+    if (n > 0 && !positions) return fail(IRIS_ERR_INVALID, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(state) + 2;
+    if (reset) {
+        static const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+        CUDA_TRY(cudaMemcpyAsync(keys, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    if (n > 0) {
+        const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+        k_slf_bounds<<<grid, 256, 0, st>>>(positions, valid, n, keys);
+        LAUNCHED();
+    }
+    k_slf_bounds_decode<<<1, 1, 0, st>>>(keys, state);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+static int slf_grid_ok(float vrange, int32_t H) {
+    if (!(vrange > 0.f) || H < 1 || H > 1024) return fail(IRIS_ERR_INVALID, "bad SLF grid (range must be > 0, 1 <= H <= 1024)");
+    return IRIS_OK;
+}
+
+int iris_slf_mark(const float *positions, const uint8_t *valid, int64_t n, float voxel_min, float voxel_range, int32_t H, int32_t *occupancy,
+                  void *stream) {
+    int rc = slf_grid_ok(voxel_range, H);
+    if (rc) return rc;
+    if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
+    if (n == 0) return IRIS_OK;
+    if (!positions || !occupancy) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_slf_mark<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(positions, valid, n, voxel_min, voxel_range, H, occupancy);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int64_t iris_slf_index_workspace_bytes(int32_t H) {
+    const int64_t cells = (int64_t)H * H * H;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (int)cells);
+    return 4 * cells + ((int64_t)tmp + 255) / 256 * 256 + 256;
+}
+
+int iris_slf_index(const int32_t *occupancy, int32_t H, int32_t *inds, int64_t *n_cells, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (H < 1 || H > 1024) return fail(IRIS_ERR_INVALID, "bad SLF grid");
+    if (!occupancy || !inds || !n_cells || !workspace) return fail(IRIS_ERR_INVALID, "NULL array");
+    if (workspace_bytes < iris_slf_index_workspace_bytes(H)) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)H * H * H;
+    int32_t *rank = reinterpret_cast<int32_t *>(workspace);
+    void *tmp = reinterpret_cast<unsigned char *>(workspace) + ((4 * cells + 255) / 256) * 256;
+    size_t tmp_bytes = (size_t)(workspace_bytes - ((4 * cells + 255) / 256) * 256);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, occupancy, rank, (int)cells, st));
+    g_launches.fetch_add(1);
+    k_slf_index<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(occupancy, rank, cells, inds);
+    LAUNCHED();
+    int32_t last_rank = 0, last_occ = 0;
+    CUDA_TRY(cudaMemcpyAsync(&last_rank, rank + cells - 1, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&last_occ, occupancy + cells - 1, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *n_cells = (int64_t)last_rank + (last_occ ? 1 : 0);
+    return IRIS_OK;
+}
+
+int iris_slf_accumulate(const float *positions, const uint8_t *valid, const float *radiance, int64_t n, float voxel_min, float voxel_range, int32_t H,
+                        const int32_t *inds, float *sum, int32_t *count, void *stream) {
+    int rc = slf_grid_ok(voxel_range, H);
+    if (rc) return rc;
+    if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
+    if (n == 0) return IRIS_OK;
+    if (!positions || !radiance || !inds || !sum || !count) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_slf_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(positions, valid, radiance, n, voxel_min, voxel_range, H, inds, sum, count);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_slf_finalize(float *sum, const int32_t *count, int64_t n_cells, void *stream) {
+    if (n_cells < 0) return fail(IRIS_ERR_INVALID, "n_cells < 0");
+    if (n_cells == 0) return IRIS_OK;
+    if (!sum || !count) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_slf_finalize<<<(unsigned)((3 * n_cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sum, count, n_cells);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
 int iris_brdf_shading_forward(const float *mat, const float *diffuse, const float *specular0, const float *specular1, int32_t n_levels, int64_t n,
                               float *L, void *stream) {
     if (n < 0 || n_levels < 2) return fail(IRIS_ERR_INVALID, "bad brdf_shading arguments");

@@ -69,3 +69,21 @@ def shading_inputs(n=4096, R=6, seed=21):
     specular1 = torch.rand(n, R, 3, generator=g) * 0.5
     dL = torch.randn(n, 3, generator=g)
     return dict(albedo=albedo, roughness=roughness, metallic=metallic, diffuse=diffuse, specular0=specular0, specular1=specular1, dL=dL)
+
+
+def slf_inputs(n_views=3, n=30000, seed=33):
+    """Seeded inputs of the SLF-bake case: per view, points in a box (with a few far outliers on one view so that the bounds are
+    not symmetric), a validity mask with ~10% misses, radiance.  One view has no valid point at all."""
+    g = torch.Generator().manual_seed(seed)
+    views, rads = [], []
+    for v in range(n_views + 1):
+        pos = torch.rand(n, 3, generator=g) * torch.tensor([3.0, 2.4, 3.4]) + torch.tensor([-1.2, 0.1, -0.9])
+        valid = torch.rand(n, generator=g) > 0.1
+        if v == 1:
+            pos[:5] = torch.tensor([[2.6, 2.9, -1.4], [-1.45, 0.0, 0.0], [0.0, 0.0, 2.95], [1.0, 1.0, 1.0], [1.0, 1.0, 1.0]])
+            valid[:5] = True
+        if v == n_views:
+            valid[:] = False
+        views.append((pos, valid))
+        rads.append(torch.rand(n, 3, generator=g) * 4.0)
+    return views, rads

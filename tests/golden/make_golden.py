@@ -56,9 +56,40 @@ def shading_golden():
     print("shading.npz", {k: v.shape for k, v in g.items()})
 
 
+def slf_golden():
+    """tests/golden/slf.npz: the SLF bake of slf_bake.py:70-145 with the reference's OWN VoxelSLF (model/slf.py, imported from
+    /root/reference through the harness) on the seeded points of cases.slf_inputs()."""
+    from oracle import slf as OSLF
+    ref_slf = RH.load_reference()["slf"].VoxelSLF
+
+    class RefSLF:                                          # adapter: nn.Module buffers -> the attributes oracle.slf.bake reads
+        def __init__(self, mask, vmin, vmax):
+            self.m = ref_slf(mask, vmin, vmax)
+
+        def scatter_add(self, x, r):
+            self.m.scatter_add(x, r)
+
+        inds = property(lambda s: s.m.inds)
+        count = property(lambda s: s.m.count)
+        radiance = property(lambda s: s.m.radiance, lambda s, v: setattr(s.m, "radiance", v))
+
+    H = 32
+    views, rads = cases.slf_inputs()
+    out = OSLF.bake(views, rads, H, "synthetic", slf_cls=RefSLF)
+    own = OSLF.bake(views, rads, H, "synthetic")
+    assert torch.equal(out["weight"]["inds"], own["weight"]["inds"]) and torch.equal(out["weight"]["count"], own["weight"]["count"])
+    assert torch.equal(out["weight"]["radiance"], own["weight"]["radiance"]) and torch.equal(out["mask"], own["mask"])
+    g = dict(voxel_min=np.float64(out["voxel_min"]), voxel_max=np.float64(out["voxel_max"]), mask=np.packbits(out["mask"].numpy().reshape(-1)),
+             inds=out["weight"]["inds"].numpy().astype(np.int32), radiance=out["weight"]["radiance"].numpy(), count=out["weight"]["count"].numpy().astype(np.int32))
+    np.savez_compressed(os.path.join(HERE, "slf.npz"), **g)
+    print("slf.npz", {k: getattr(v, "shape", v) for k, v in g.items()}, "cells", len(g["count"]))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "shading":
         return shading_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "slf":
+        return slf_golden()
     out = {}
     # ---------------- small: every estimator
     c = cases.build("small")
@@ -95,6 +126,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "c1.npz"), **g)
     print("c1.npz", {k: v.shape for k, v in g.items()})
     shading_golden()
+    slf_golden()
 
 
 if __name__ == "__main__":

@@ -166,3 +166,17 @@ def test_shading_oracle_matches_reference_golden():
     assert np.array_equal(a.grad.numpy(), g["d_albedo"]) and np.array_equal(r.grad.numpy(), g["d_roughness"]) and np.array_equal(m.grad.numpy(), g["d_metallic"])
     with torch.no_grad():
         assert np.array_equal(OS.lerp_specular(x["specular0"], x["roughness"]).numpy(), g["lerp0"])
+
+
+def test_slf_bake_oracle_matches_reference_golden():
+    """oracle/slf.py (slf_bake.py:70-145, model/slf.py:16-61) against tests/golden/slf.npz, produced with the reference's own VoxelSLF."""
+    import torch
+    from oracle import slf as OSLF
+    from tests.golden import cases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "slf.npz"))
+    views, rads = cases.slf_inputs()
+    out = OSLF.bake(views, rads, 32, "synthetic")
+    assert out["voxel_min"] == float(g["voxel_min"]) and out["voxel_max"] == float(g["voxel_max"])
+    assert np.array_equal(np.packbits(out["mask"].numpy().reshape(-1)), g["mask"])
+    assert np.array_equal(out["weight"]["inds"].numpy(), g["inds"]) and np.array_equal(out["weight"]["count"].numpy(), g["count"])
+    assert np.array_equal(out["weight"]["radiance"].numpy(), g["radiance"])
