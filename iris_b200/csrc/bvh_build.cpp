@@ -120,10 +120,10 @@ struct Builder {
 };
 
 inline uint8_t exp_for_extent(double ext) {
-    // smallest e with ext / 2^e <= 255
+    // smallest e with ext / 2^e <= BVH8_QMAX
     if (!(ext > 0.0)) return (uint8_t)1;   // 2^-126
-    int e = (int)std::ceil(std::log2(ext / 255.0));
-    while (std::ldexp(255.0, e) < ext) ++e;
+    int e = (int)std::ceil(std::log2(ext / (double)BVH8_QMAX));
+    while (std::ldexp((double)BVH8_QMAX, e) < ext) ++e;
     e = std::max(-126, std::min(127, e));
     return (uint8_t)(e + 127);
 }
@@ -272,13 +272,13 @@ int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, in
             const Node2 &c = B.nodes[ch[i]];
             const uint8_t *dummy = nullptr;
             (void)dummy;
-            uint8_t *qlo[3] = {N.qlo_x, N.qlo_y, N.qlo_z}, *qhi[3] = {N.qhi_x, N.qhi_y, N.qhi_z};
+            bvh8_q_t *qlo[3] = {N.qlo_x, N.qlo_y, N.qlo_z}, *qhi[3] = {N.qhi_x, N.qhi_y, N.qhi_z};
             for (int k = 0; k < 3; ++k) {
                 double sc = std::ldexp(1.0, (int)N.e[k] - 127);
                 double lo = std::floor(((double)c.box.lo[k] - (double)N.p[k]) / sc);
                 double hi = std::ceil(((double)c.box.hi[k] - (double)N.p[k]) / sc);
-                qlo[k][s] = (uint8_t)std::max(0.0, std::min(255.0, lo));
-                qhi[k][s] = (uint8_t)std::max(0.0, std::min(255.0, hi));
+                qlo[k][s] = bvh8_encode_q((int)std::max(0.0, std::min((double)BVH8_QMAX, lo)));
+                qhi[k][s] = bvh8_encode_q((int)std::max(0.0, std::min((double)BVH8_QMAX, hi)));
             }
             if (c.total > kMaxLeaf) {
                 N.imask |= (uint8_t)(1u << s);

@@ -182,8 +182,8 @@ __device__ __forceinline__ int lbvh_first(const LbvhNodes &N, int n, int node) {
 
 __device__ __forceinline__ uint8_t dev_exp_for_extent(double ext) {
     if (!(ext > 0.0)) return (uint8_t)1;
-    int e = (int)ceil(log2(ext / 255.0));
-    while (ldexp(255.0, e) < ext) ++e;
+    int e = (int)ceil(log2(ext / (double)BVH8_QMAX));
+    while (ldexp((double)BVH8_QMAX, e) < ext) ++e;
     e = max(-126, min(127, e));
     return (uint8_t)(e + 127);
 }
@@ -265,11 +265,11 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
         const int i = child_in_slot[s];
         if (i < 0) continue;
         const DBox b = N.box[ch[i]];
-        uint8_t *qlo[3] = {O.qlo_x, O.qlo_y, O.qlo_z}, *qhi[3] = {O.qhi_x, O.qhi_y, O.qhi_z};
+        bvh8_q_t *qlo[3] = {O.qlo_x, O.qlo_y, O.qlo_z}, *qhi[3] = {O.qhi_x, O.qhi_y, O.qhi_z};
         for (int a = 0; a < 3; ++a) {
             const double sc = ldexp(1.0, (int)O.e[a] - 127);
-            qlo[a][s] = (uint8_t)fmax(0.0, fmin(255.0, floor(((double)b.lo[a] - (double)O.p[a]) / sc)));
-            qhi[a][s] = (uint8_t)fmax(0.0, fmin(255.0, ceil(((double)b.hi[a] - (double)O.p[a]) / sc)));
+            qlo[a][s] = bvh8_encode_q((int)fmax(0.0, fmin((double)BVH8_QMAX, floor(((double)b.lo[a] - (double)O.p[a]) / sc))));
+            qhi[a][s] = bvh8_encode_q((int)fmax(0.0, fmin((double)BVH8_QMAX, ceil(((double)b.hi[a] - (double)O.p[a]) / sc))));
         }
         const int c = lbvh_count(N, n, ch[i]);
         if (c > 3) {

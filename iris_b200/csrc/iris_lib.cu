@@ -490,7 +490,10 @@ int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t 
     return launch_field(P, n, position, mat, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-#define FIELD_BWD_CHUNK (1ll << 20)
+#ifndef FIELD_BWD_CHUNK_LOG2
+#define FIELD_BWD_CHUNK_LOG2 22
+#endif
+#define FIELD_BWD_CHUNK (1ll << FIELD_BWD_CHUNK_LOG2)
 static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *position, const float4 *r5, const float *d_mat, float *d_params,
                               void *workspace, int64_t workspace_bytes, cudaStream_t st, __half *x_saved = nullptr) {
     static bool attr_done = false;

@@ -82,6 +82,39 @@ __device__ __forceinline__ void slab_pair(uint32_t w, int j, float a, float c, f
 }
 #endif
 
+#if IRIS_NODE_FP16
+// one 32-bit word = the fp16 plane coordinates of two children -> out[k] = fma(q_k, a, b)
+__device__ __forceinline__ void slab_pair_h(uint32_t w, float a, float b, float (&out)[2]) {
+#ifdef IRIS_HOST_EMULATION
+    out[0] = fmaf((float)bvh8_decode_q((bvh8_q_t)(w & 0xFFFFu)), a, b);
+    out[1] = fmaf((float)bvh8_decode_q((bvh8_q_t)(w >> 16)), a, b);
+#else
+    float v0, v1;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(v0), "=f"(v1) : "r"(w));
+    unsigned long long v, aa, bb, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(v), "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(out[0]), "=f"(out[1]) : "l"(r));
+#endif
+}
+// 16-byte word `w` (a per-ray register: the near or far plane word of an axis) of the node at np.  The address is formed with one
+// IMAD.WIDE on the FMA pipe, so picking near/far by the ray's sign costs no ALU-pipe work (SELs on the loaded words would cost 24).
+__device__ __forceinline__ uint4 load_plane_word(const float4 *np, uint32_t w) {
+#ifdef IRIS_HOST_EMULATION
+    const float4 a = ldg4(np + w);
+    return make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+#else
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(w), "l"(np));
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
+    return r;
+#endif
+}
+#endif
+
 // Moller-Trumbore barycentrics + projected t, operation order of oracle/intersect.c:tri_test (rdd = 1/(d.d))
 __device__ __forceinline__ bool tri_test(f3 o, f3 d, float rdd, f3 v0, f3 e1, f3 e2, float &t, float &u, float &v) {
     f3 p = xcross(d, e2);
@@ -138,7 +171,12 @@ __device__ __forceinline__ Hit trace_ray(const SceneView &S, f3 o, f3 d, float t
 // kernel that refills finished lanes with new rays (k_trace_persistent).
 struct TravState {
     f3 o, d;
+#if IRIS_NODE_FP16
+    uint32_t nwx, nwy, nwz;    // node word holding the NEAR planes of each axis (2,3,4 for positive directions, 7,6,5 for negative)
+    float idx, idy, idz, rdd;
+#else
     float sx, sy, sz, idx, idy, idz, rdd;
+#endif
     uint32_t octinv;
     uint2 ngroup, tgroup;
     int sp;
@@ -157,13 +195,20 @@ __device__ __forceinline__ void trav_init(TravState &T, f3 o, f3 d, float t_limi
     T.sp = 0;
     T.anyhit = anyhit;
     T.done = false;
-    T.sx = fabsf(d.x) < 1e-30f ? copysignf(1e-30f, d.x) : d.x;
-    T.sy = fabsf(d.y) < 1e-30f ? copysignf(1e-30f, d.y) : d.y;
-    T.sz = fabsf(d.z) < 1e-30f ? copysignf(1e-30f, d.z) : d.z;
-    T.idx = 1.0f / T.sx;
-    T.idy = 1.0f / T.sy;
-    T.idz = 1.0f / T.sz;
-    T.octinv = (T.sx < 0.f ? 0u : 4u) | (T.sy < 0.f ? 0u : 2u) | (T.sz < 0.f ? 0u : 1u);
+    const float sx = fabsf(d.x) < 1e-30f ? copysignf(1e-30f, d.x) : d.x;
+    const float sy = fabsf(d.y) < 1e-30f ? copysignf(1e-30f, d.y) : d.y;
+    const float sz = fabsf(d.z) < 1e-30f ? copysignf(1e-30f, d.z) : d.z;
+    T.idx = 1.0f / sx;
+    T.idy = 1.0f / sy;
+    T.idz = 1.0f / sz;
+    T.octinv = (sx < 0.f ? 0u : 4u) | (sy < 0.f ? 0u : 2u) | (sz < 0.f ? 0u : 1u);
+#if IRIS_NODE_FP16
+    T.nwx = sx < 0.f ? 7u : 2u;
+    T.nwy = sy < 0.f ? 6u : 3u;
+    T.nwz = sz < 0.f ? 5u : 4u;
+#else
+    T.sx = sx; T.sy = sy; T.sz = sz;
+#endif
     T.rdd = __fdiv_rn(1.0f, xdot(d, d));
     T.ngroup = make_uint2(0u, 0x80000000u);
     T.tgroup = make_uint2(0u, 0u);
@@ -183,7 +228,52 @@ __device__ __forceinline__ void trav_step(const SceneView &S, TravState &T, uint
         }
         const uint32_t slot = (bit - 24u) ^ T.octinv;
         const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-        const float4 *np = S.nodes + 5 * (int64_t)(base + rel);
+#if IRIS_NODE_FP16
+        const float4 *np = S.nodes + BVH8_NODE_F4 * (int64_t)(base + rel);
+        const float4 n0 = ldg4(np), n1 = ldg4(np + 1);
+        // near / far plane words per axis (8 fp16 each = children 0..7): words lo_x lo_y lo_z hi_z hi_y hi_x = 2..7, near + far = 9
+        const uint4 nx = load_plane_word(np, T.nwx), fx = load_plane_word(np, 9u - T.nwx);
+        const uint4 ny = load_plane_word(np, T.nwy), fy = load_plane_word(np, 9u - T.nwy);
+        const uint4 nz = load_plane_word(np, T.nwz), fz = load_plane_word(np, 9u - T.nwz);
+        const uint32_t ew = __float_as_uint(n0.w);
+        T.ngroup.x = __float_as_uint(n1.x);
+        T.tgroup.x = __float_as_uint(n1.y);
+        const float ax = __uint_as_float((ew & 0xFFu) << 23) * T.idx;
+        const float ay = __uint_as_float(((ew >> 8) & 0xFFu) << 23) * T.idy;
+        const float az = __uint_as_float(((ew >> 16) & 0xFFu) << 23) * T.idz;
+        const float bx = (n0.x - T.o.x) * T.idx, by = (n0.y - T.o.y) * T.idy, bz = (n0.z - T.o.z) * T.idz;
+        const uint32_t nxw[4] = {nx.x, nx.y, nx.z, nx.w}, fxw[4] = {fx.x, fx.y, fx.z, fx.w};
+        const uint32_t nyw[4] = {ny.x, ny.y, ny.z, ny.w}, fyw[4] = {fy.x, fy.y, fy.z, fy.w};
+        const uint32_t nzw[4] = {nz.x, nz.y, nz.z, nz.w}, fzw[4] = {fz.x, fz.y, fz.z, fz.w};
+        uint32_t hitmask = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
+            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {               // two children per word: HADD2.F32 x2 + one FFMA2 per plane pair
+                const int wd = 2 * h + jj;
+                float t0x[2], t1x[2], t0y[2], t1y[2], t0z[2], t1z[2];
+                slab_pair_h(nxw[wd], ax, bx, t0x); slab_pair_h(fxw[wd], ax, bx, t1x);
+                slab_pair_h(nyw[wd], ay, by, t0y); slab_pair_h(fyw[wd], ay, by, t1y);
+                slab_pair_h(nzw[wd], az, bz, t0z); slab_pair_h(fzw[wd], az, bz, t1z);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float tn = fmaxf(fmaxf(t0x[k], t0y[k]), fmaxf(t0z[k], 0.0f));
+                    const float tf = fminf(fminf(t1x[k], t1y[k]), fminf(t1z[k], T.best.t));
+                    if (tn <= tf) {
+                        const uint32_t cb = (child_bits4 >> (8 * (2 * jj + k))) & 0xFFu;
+                        const uint32_t bi = (bit_index4 >> (8 * (2 * jj + k))) & 0xFFu;
+                        hitmask |= cb << bi;
+                    }
+                }
+            }
+        }
+#else
+        const float4 *np = S.nodes + BVH8_NODE_F4 * (int64_t)(base + rel);
         const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
         const uint32_t ew = __float_as_uint(n0.w);
         T.ngroup.x = __float_as_uint(n1.x);
@@ -244,6 +334,7 @@ __device__ __forceinline__ void trav_step(const SceneView &S, TravState &T, uint
             }
 #endif
         }
+#endif
         T.ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
         T.tgroup.y = hitmask & 0x00FFFFFFu;
     } else {
