@@ -78,6 +78,7 @@ static int g_tc5_ctas = 4;      // tcgen05 kernel: CTAs per SM (34.9 KB smem, 64
 static int g_single_impl = 1;      // 1: wavefront bounce (k_single_gen -> k_trace_queue -> k_single_shade), 0: fused k_bounce_single
 static int64_t g_single_chunk = 8 << 20;   // samples per wavefront chunk
 static int g_bake_impl = 0;        // 0: fused k_bake with block-level direction sort (measured faster: 2.75 vs 2.13 G rays/s on c2), 1: ray queue
+static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
 static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
 static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
@@ -200,6 +201,17 @@ int64_t iris_launch_count(void) { return g_launches.load(); }
 int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "field_forward_impl") == 0 && (value == 0 || value == 1)) { g_field_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "intersect_impl") == 0 && (value == 0 || value == 1)) { g_intersect_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "trace_smem_carveout_pct") == 0 && value >= -1 && value <= 100) {
+        // shared-memory share of the SM's 228 KB for the tracing kernels (they use none, or 14 KB for the bake sort): -1 = driver default, 0 = all L1
+        CUDA_TRY(cudaFuncSetAttribute(k_trace_queue, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_intersect, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_intersect_persistent, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_primary, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_bake<0>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CUDA_TRY(cudaFuncSetAttribute(k_bake<1>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        return IRIS_OK;
+    }
+    if (name && std::strcmp(name, "wave_impl") == 0 && (value == 0 || value == 1)) { g_wave_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "bake_impl") == 0 && (value == 0 || value == 1)) { g_bake_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
@@ -661,16 +673,53 @@ static int wave_field(const IrisShadeParams *P, int64_t n, float4 *pos, float4 *
     return launch_field(P, n, nullptr, nullptr, pos, m1, m2, st);
 }
 
+// one "bounce a" of the wavefront estimators: fused kernel (wave_impl 0) or generate -> ray-queue trace -> resolve (default)
+#define WAVE_KIND_SWITCH(KERNEL, ...)                                                         \
+    switch (kind) {                                                                           \
+    case 0: KERNEL<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(__VA_ARGS__); break;               \
+    case 1: KERNEL<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(__VA_ARGS__); break;               \
+    case 2: KERNEL<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(__VA_ARGS__); break;               \
+    default: KERNEL<3><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(__VA_ARGS__); break;              \
+    }
+static int wave_bounce_a(int kind, const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int col0, float level, int64_t n, WaveState W,
+                         cudaStream_t st) {
+    if (g_wave_impl == 0) {
+        ProfScope ps(K_WAVE_A, st);
+        WAVE_KIND_SWITCH(k_wave_bounce_a, view_of(s), *P, *smp, col0, level, n, W)
+        LAUNCHED();
+        return IRIS_OK;
+    }
+    CUDA_TRY(cudaMemsetAsync(W.counter, 0, 8, st));
+    {
+        ProfScope ps(K_WAVE_A, st);
+        WAVE_KIND_SWITCH(k_wave_gen, *P, *smp, col0, level, n, W)
+    }
+    LAUNCHED();
+    {
+        ProfScope ps(K_TRACE_QUEUE, st);
+        const bool shadow = kind <= 1;                       // det_*: only the closest-hit half of the queue is populated
+        const float4 *ro = shadow ? W.RO : W.RO + n, *rd = shadow ? W.RD : W.RD + n;
+        float4 *hit = shadow ? W.HIT : W.HIT + n;
+        const int64_t nr = shadow ? 2 * n : n;
+        const int grid = (int)std::min<int64_t>(blocks_for(nr), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
+        k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, nr, shadow ? n : 0, hit, W.counter);
+    }
+    LAUNCHED();
+    {
+        ProfScope ps(K_WAVE_A, st);
+        WAVE_KIND_SWITCH(k_wave_resolve, view_of(s), n, W)
+    }
+    LAUNCHED();
+    return IRIS_OK;
+}
+
 // one indirect depth (trace_indirect loop body) on the current state
 static int wave_indirect(const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int64_t n, WaveState W, int depth, int col_base,
                          cudaStream_t st) {
     for (int k = 0; k < depth; ++k) {
-        {
-            ProfScope ps(K_WAVE_A, st);
-            k_wave_bounce_a<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, col_base + 6 * k, 0.f, n, W);
-        }
-        LAUNCHED();
-        int rc = wave_field(P, n, W.H0, W.M1, W.M2, st);
+        int rc = wave_bounce_a(1, s, P, smp, col_base + 6 * k, 0.f, n, W, st);
+        if (rc) return rc;
+        rc = wave_field(P, n, W.H0, W.M1, W.M2, st);
         if (rc) return rc;
         {
             ProfScope ps(K_WAVE_B, st);
@@ -709,11 +758,7 @@ int iris_path_tracing(const IrisScene *s, const IrisShadeParams *P, const float 
     }
     LAUNCHED();
     if ((rc = wave_field(P, n, W.S0, W.S1, W.S2, st))) return rc;
-    {
-        ProfScope ps(K_WAVE_A, st);
-        k_wave_bounce_a<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, 2, 0.f, n, W);
-    }
-    LAUNCHED();
+    if ((rc = wave_bounce_a(0, s, P, smp, 2, 0.f, n, W, st))) return rc;
     if ((rc = wave_field(P, n, W.H0, W.M1, W.M2, st))) return rc;
     {
         ProfScope ps(K_WAVE_B, st);
@@ -747,12 +792,7 @@ int iris_path_tracing_det(const IrisScene *s, const IrisShadeParams *P, int mode
         k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(positions, wis, 1, normals, prim, n_pixels, spp, W);
     }
     LAUNCHED();
-    {
-        ProfScope ps(K_WAVE_A, st);
-        if (mode == 0) k_wave_bounce_a<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, 0, 0.f, n, W);
-        else k_wave_bounce_a<3><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, 0, roughness_level, n, W);
-    }
-    LAUNCHED();
+    if ((rc = wave_bounce_a(mode == 0 ? 2 : 3, s, P, smp, 0, mode == 0 ? 0.f : roughness_level, n, W, st))) return rc;
     if ((rc = wave_field(P, n, W.H0, W.M1, W.M2, st))) return rc;
     {
         ProfScope ps(K_WAVE_B, st);

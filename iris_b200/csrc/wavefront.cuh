@@ -22,13 +22,21 @@ struct WaveState {
     float4 *H2;   // sampled wi.xyz | hit prim (int bits)
     float4 *M1;   // material at next hit:  - | metallic
     float4 *M2;   // material at next hit: albedo.rgb | roughness
+    // ray queue of one bounce (k_wave_gen -> k_trace_queue -> k_wave_resolve): lane i owns shadow ray i and closest-hit ray n + i
+    float4 *RO;   // 2n: origin | t_limit (< 0 = empty slot)
+    float4 *RD;   // 2n: direction | prim_limit
+    float4 *HIT;  // 2n: t u v | slot
+    float4 *PN;   // n: emitter-sample contribution to add if the shadow ray is unoccluded | bsdf pdf
+    unsigned long long *counter;
 };
-#define WAVE_STREAMS 14
+#define WAVE_STREAMS 22   // 14 state + 7 queue streams per lane (+ one stream's worth of slack that holds the fetch counter)
 __host__ __device__ inline WaveState wave_carve(void *base, int64_t n) {
     float4 *p = reinterpret_cast<float4 *>(base);
     WaveState w;
     w.S0 = p; w.S1 = p + n; w.S2 = p + 2 * n; w.S3 = p + 3 * n; w.S4 = p + 4 * n; w.S5 = p + 5 * n; w.S6 = p + 6 * n; w.S7 = p + 7 * n;
     w.S8 = p + 8 * n; w.H0 = p + 9 * n; w.H1 = p + 10 * n; w.H2 = p + 11 * n; w.M1 = p + 12 * n; w.M2 = p + 13 * n;
+    w.RO = p + 14 * n; w.RD = p + 16 * n; w.HIT = p + 18 * n; w.PN = p + 20 * n;
+    w.counter = reinterpret_cast<unsigned long long *>(p + 21 * n);
     return w;
 }
 
@@ -181,6 +189,105 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_a(SceneView S, IrisS
     hit_surface(S, h, wi, hp, hn);
     W.H0[i] = make_float4(hp.x, hp.y, hp.z, __int_as_float(h.prim >= 0 ? -2 : -1));
     W.H1[i] = make_float4(hn.x, hn.y, hn.z, bpdf);
+    W.H2[i] = make_float4(wi.x, wi.y, wi.z, __int_as_float(h.prim));
+}
+
+// ---- the same bounce through the ray queue: k_wave_gen writes the two rays of a lane and the emitter-sample contribution that is
+// pending on the shadow ray, k_trace_queue (kernels.cuh) traces, k_wave_resolve applies the contribution and stores the next hit.
+template <int KIND>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, IrisSampler smp, int col0, float level, int64_t n, WaveState W) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 empty = make_float4(0.f, 0.f, 0.f, -1.f);
+    const float4 s0 = W.S0[i];
+    if (__float_as_int(s0.w) != -2) { W.RO[i] = empty; W.RO[n + i] = empty; return; }
+    const f3 x0 = mk3(s0.x, s0.y, s0.z), n0 = ld4(W.S1, i), wo = ld4(W.S3, i);
+    float u[6];
+    sample_cols6(smp, i, col0, u);
+    f3 wi, bw = mk3(1.f, 1.f, 1.f);
+    float bpdf = 0.f;
+    float4 ro_s = empty, rd_s = empty;
+    f3 pend = mk3(0.f, 0.f, 0.f);
+    if (KIND <= 1) {
+        Mat mat;
+        const float4 m2 = W.S2[i];
+        mat.a = mk3(m2.x, m2.y, m2.z);
+        mat.r = m2.w;
+        mat.m = W.S1[i].w;
+        const float clampv = KIND == 0 ? 1e-6f : 1e-12f;
+        {
+            f3 wl;
+            float pdf_e;
+            int32_t e, face;
+            sample_emitter(P, u[0], u[1], u[2], x0, wl, pdf_e, e, face);
+            const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wl.x, x0.y + IRIS_RAY_EPSILON * wl.y, x0.z + IRIS_RAY_EPSILON * wl.z);
+            f3 v0, e1, e2;
+            emitter_triangle(P, e, v0, e1, e2);
+            float tl, bu, bv;
+            if (tri_test(org, wl, __fdiv_rn(1.0f, xdot(wl, wl)), v0, e1, e2, tl, bu, bv)) {
+                ro_s = make_float4(org.x, org.y, org.z, tl);
+                rd_s = make_float4(wl.x, wl.y, wl.z, __int_as_float(face));
+                Hit h;
+                h.t = tl; h.u = bu; h.v = bv; h.prim = face; h.slot = -1;
+                f3 hp, hn;
+                surface_from_triangle(h, wl, v0, e1, e2, hp, hn);
+                const f3 dlt = hp - x0;
+                const float G = fabsf(-(wl.x * hn.x) - (wl.y * hn.y) - (wl.z * hn.z)) / fmaxf(dot(dlt, dlt), clampv);
+                f3 f;
+                float pb;
+                eval_brdf<false>(wl, wo, n0, mat, f, pb, nullptr);
+                pb *= G;
+                float w = (pdf_e > 0.f && !isinf(pb)) ? pdf_e * pdf_e / (pdf_e * pdf_e + pb * pb) : 0.f;
+                if (isinf(pdf_e) || pb == 0.f) w = 1.f;
+                const f3 c = f * (emitter_radiance(P, e) * (G / fmaxf(pdf_e, clampv) * w));
+                pend = KIND == 0 ? c : nan0(ld4(W.S4, i) * c);
+            }
+        }
+        sample_brdf<false>(u[3], u[4], u[5], wo, n0, mat, wi, bpdf, bw, nullptr);
+        if (KIND == 0) {
+            W.S7[i] = make_float4(bw.x, bw.y, bw.z, 0.f);
+        } else {
+            const f3 t = ld4(W.S4, i) * bw;
+            W.S4[i] = make_float4(t.x, t.y, t.z, 0.f);
+        }
+    } else if (KIND == 2) {
+        wi = diffuse_sampler(u[0], u[1], n0);
+        W.S7[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    } else {
+        wi = specular_sampler(u[0], u[1], level, wo, n0);
+        float w0, w1;
+        specular_weights(wi, wo, n0, level, w0, w1);
+        W.S7[i] = make_float4(w0, w0, w0, 0.f);
+        W.S8[i] = make_float4(w1, w1, w1, 0.f);
+    }
+    W.RO[i] = ro_s;
+    W.RD[i] = rd_s;
+    W.RO[n + i] = make_float4(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
+    W.RD[n + i] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
+    W.PN[i] = make_float4(pend.x, pend.y, pend.z, bpdf);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_resolve(SceneView S, int64_t n, WaveState W) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (__float_as_int(W.S0[i].w) != -2) { W.H0[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); return; }
+    const float4 pn = W.PN[i];
+    if (KIND <= 1 && W.RO[i].w >= 0.f && __float_as_int(W.HIT[i].w) < 0) {      // shadow ray cast and unoccluded
+        if (KIND == 0) {
+            const f3 a = ld4(W.S6, i) + mk3(pn.x, pn.y, pn.z);
+            W.S6[i] = make_float4(a.x, a.y, a.z, 0.f);
+        } else {
+            const f3 a = ld4(W.S5, i) + mk3(pn.x, pn.y, pn.z);
+            W.S5[i] = make_float4(a.x, a.y, a.z, 0.f);
+        }
+    }
+    const float4 dq = W.RD[n + i];
+    const f3 wi = mk3(dq.x, dq.y, dq.z);
+    f3 hp, hn;
+    const Hit h = queue_hit_surface(S, W.HIT[n + i], wi, hp, hn);
+    W.H0[i] = make_float4(hp.x, hp.y, hp.z, __int_as_float(h.prim >= 0 ? -2 : -1));
+    W.H1[i] = make_float4(hn.x, hn.y, hn.z, pn.w);
     W.H2[i] = make_float4(wi.x, wi.y, wi.z, __int_as_float(h.prim));
 }
 

@@ -26,13 +26,16 @@ def main():
     rd = torch.nn.functional.normalize(torch.randn(N, 3, device=dev, generator=g), dim=-1)
     pops = {"primary": (o, d), "secondary": (so.contiguous(), sd.contiguous()), "random": (ro, rd)}
     out = {}
+    import os
+    if os.environ.get("IRIS_CARVEOUT"):
+        core.C.check(lib.iris_set_option(b"trace_smem_carveout_pct", int(os.environ["IRIS_CARVEOUT"])))
     for name, (a, b) in pops.items():
         core.C.check(lib.iris_set_option(b"intersect_impl", 0))
         ref = scene.intersect_raw(a, b)
         ms0 = ev_time(lambda: scene.intersect_raw(a, b), 5, 2)
         out[name + "_base"] = round(a.shape[0] / ms0 / 1e3, 1)
         core.C.check(lib.iris_set_option(b"intersect_impl", 1))
-        for ctas in (4, 8, 12):
+        for ctas in (8,):
             core.C.check(lib.iris_set_option(b"persist_ctas_per_sm", ctas))
             got = scene.intersect_raw(a, b)
             same = all(bool(torch.equal(x, y)) for x, y in zip(ref, got))
