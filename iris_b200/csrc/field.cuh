@@ -427,6 +427,10 @@ __device__ __forceinline__ void warp_gemm_t(const __half *A, int lda, const __ha
 __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
+// 16-byte reduction (sm_90+): two adjacent grid entries at once; addr must be 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // WS = true: positions/flags from the estimator record word r5 (x0.xyz, code), d_mat from the workspace; WS = false: plain arrays
 template <bool WS>
@@ -732,8 +736,22 @@ __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams 
                     if ((lane & 3u) == 0u) red_add_v2(d_grid + 2 * (int64_t)(L.offset + id), rx, ry);
                 }
             } else if (has) {
+#ifndef FIELD_SCATTER_NO_V4
+                if (l >= FIELD_DENSE_LEVELS && (cx & 1u) == 0u) {
+                    // hashed level, even cell x: corners c and c+1 (x and x+1, same y z) hash to idx and idx ^ 1 -- the two halves of one
+                    // aligned 16-byte slot of the gradient table -- so four 16-byte reductions replace eight 8-byte ones
 #pragma unroll
-                for (int c = 0; c < 8; ++c) red_add_v2(d_grid + 2 * (int64_t)(L.offset + idxc[c]), wc[c] * gx, wc[c] * gy);
+                    for (int c = 0; c < 8; c += 2) {
+                        const bool swap = idxc[c] & 1u;                                 // the even-x corner sits in the odd entry
+                        const float ax = wc[c] * gx, ay = wc[c] * gy, bx = wc[c + 1] * gx, by = wc[c + 1] * gy;
+                        red_add_v4(d_grid + 2 * (int64_t)(L.offset + (idxc[c] & ~1u)), swap ? bx : ax, swap ? by : ay, swap ? ax : bx, swap ? ay : by);
+                    }
+                } else
+#endif
+                {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add_v2(d_grid + 2 * (int64_t)(L.offset + idxc[c]), wc[c] * gx, wc[c] * gy);
+                }
             }
         }
     }
