@@ -19,6 +19,10 @@
 #pragma once
 #include <stdint.h>
 
+// largest subtree (in triangles) that becomes ONE leaf child slot; the slot's meta byte holds the count in unary (1..3)
+#ifndef IRIS_MAX_LEAF
+#define IRIS_MAX_LEAF 3
+#endif
 #ifndef IRIS_NODE_FP16
 #define IRIS_NODE_FP16 0
 #endif

@@ -33,7 +33,7 @@ struct Node2 {
 };
 
 constexpr int kBins = 16;
-constexpr int kMaxLeaf = 3;
+constexpr int kMaxLeaf = IRIS_MAX_LEAF;
 
 struct Builder {
     std::vector<Box> tbox;

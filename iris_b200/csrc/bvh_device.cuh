@@ -196,7 +196,7 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
     const int bnode = wide_bin[w];
     int ch[8];
     int nch = 0;
-    if (lbvh_count(N, n, bnode) <= 3) {
+    if (lbvh_count(N, n, bnode) <= IRIS_MAX_LEAF) {
         ch[nch++] = bnode;                                   // tiny scene: the root itself is a leaf child
     } else {
         const int2 c = N.child[bnode];
@@ -206,7 +206,7 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
             int best = -1;
             float ba = -1.f;
             for (int i = 0; i < nch; ++i)
-                if (lbvh_count(N, n, ch[i]) > 3) {
+                if (lbvh_count(N, n, ch[i]) > IRIS_MAX_LEAF) {
                     const float a = dbox_area(N.box[ch[i]]);
                     if (a > ba) { ba = a; best = i; }
                 }
@@ -246,7 +246,7 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
     int n_inner = 0, n_tris = 0;
     for (int i = 0; i < nch; ++i) {
         const int c = lbvh_count(N, n, ch[i]);
-        if (c > 3) ++n_inner; else n_tris += c;
+        if (c > IRIS_MAX_LEAF) ++n_inner; else n_tris += c;
     }
     const int child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0;
     const int tri_base = n_tris ? atomicAdd(&counters[1], n_tris) : 0;
@@ -272,7 +272,7 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
             qhi[a][s] = bvh8_encode_q((int)fmax(0.0, fmin((double)BVH8_QMAX, ceil(((double)b.hi[a] - (double)O.p[a]) / sc))));
         }
         const int c = lbvh_count(N, n, ch[i]);
-        if (c > 3) {
+        if (c > IRIS_MAX_LEAF) {
             O.imask |= (uint8_t)(1u << s);
             O.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             wide_bin[child_base + inner_i] = ch[i];

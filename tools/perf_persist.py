@@ -1,3 +1,4 @@
+import os
 """A/B: k_intersect (one ray per lane) vs k_intersect_persistent (dynamic ray fetch) on three ray populations."""
 import sys, json
 import numpy as np, torch
@@ -9,7 +10,8 @@ def main():
     dev = torch.device("cuda", 0)
     lib = core.C.lib()
     sc = scenes.room(1_000_000, 16, seed=0)
-    scene = core.Scene(sc.vertices, sc.faces, 0)
+    scene = core.Scene(sc.vertices, sc.faces, 0, builder=int(os.environ.get('IRIS_BUILDER', '1')))
+    print(scene.stats())
     rays = torch.as_tensor(sc.camera_rays(1280, 960, view=1)).to(dev)
     o, d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
     t, prim, uv, p, n = scene.intersect_raw(o, d)
@@ -26,7 +28,7 @@ def main():
     rd = torch.nn.functional.normalize(torch.randn(N, 3, device=dev, generator=g), dim=-1)
     pops = {"primary": (o, d), "secondary": (so.contiguous(), sd.contiguous()), "random": (ro, rd)}
     out = {}
-    import os
+
     if os.environ.get("IRIS_CARVEOUT"):
         core.C.check(lib.iris_set_option(b"trace_smem_carveout_pct", int(os.environ["IRIS_CARVEOUT"])))
     for name, (a, b) in pops.items():
