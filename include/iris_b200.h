@@ -201,6 +201,20 @@ int iris_slf_accumulate(const float *positions, const uint8_t *valid, const floa
 int iris_slf_finalize(float *sum, const int32_t *count, int64_t n_cells, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Emitter extraction on the device -- extract_emitter_ldr.py:76-110 (the stage that produces emitter.pth).  Device arrays.
+ *   iris_tri_accumulate    tri_sum[prim] += radiance, tri_count[prim] += 1 for every valid ray that hit a triangle (prim from
+ *                          iris_intersect; torch_scatter 'sum' in the reference, :85-90); zero both tables first.
+ *   iris_emitter_classify  is_emitter[f] = max_c(tri_sum[f][c] / max(tri_count[f], 1)) > threshold           (:92-95)
+ *   iris_emitter_geometry  for the K selected faces (emitter_faces, increasing face index = boolean-mask order): the three
+ *                          vertices (K,3,3), area = |e1 x e2| / 2 and unit normal e1 x e2 / max(|e1 x e2|, 1e-12)  (:96-100)
+ * ---------------------------------------------------------------------------------------------- */
+int iris_tri_accumulate(const int32_t *prim, const uint8_t *valid, const float *radiance, int64_t n, int64_t n_faces, float *tri_sum,
+                        int32_t *tri_count, void *stream);
+int iris_emitter_classify(const float *tri_sum, const int32_t *tri_count, int64_t n_faces, float threshold, uint8_t *is_emitter, void *stream);
+int iris_emitter_geometry(const float *verts, const int32_t *faces, const int64_t *emitter_faces, int64_t n_emitters, float *out_vertices,
+                          float *out_area, float *out_normal, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training-step shading from baked maps -- train_brdf_crf.py:193-206 with utils/ops.py:99-119 (lerp_specular):
  *   kd = albedo (1 - metallic), ks = 0.04 (1 - metallic) + albedo metallic,
  *   L = kd * diffuse + ks * lerp(specular0, roughness) + lerp(specular1, roughness)

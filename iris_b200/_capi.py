@@ -62,6 +62,9 @@ PROTOTYPES = {
     "iris_slf_index": (ctypes.c_int, [c_vp, c_i32, c_vp, ctypes.POINTER(c_i64), c_vp, c_i64, c_vp]),
     "iris_slf_accumulate": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "iris_slf_finalize": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "iris_tri_accumulate": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "iris_emitter_classify": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_vp]),
+    "iris_emitter_geometry": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "iris_brdf_shading_forward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "iris_brdf_shading_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
     "iris_crf_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp]),

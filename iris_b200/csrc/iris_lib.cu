@@ -16,6 +16,7 @@
 #include "crf.cuh"
 #include "shade_maps.cuh"
 #include "slf_bake.cuh"
+#include "emitter_extract.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -914,6 +915,36 @@ int iris_slf_finalize(float *sum, const int32_t *count, int64_t n_cells, void *s
     if (n_cells == 0) return IRIS_OK;
     if (!sum || !count) return fail(IRIS_ERR_INVALID, "NULL array");
     k_slf_finalize<<<(unsigned)((3 * n_cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sum, count, n_cells);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ emitter extraction (extract_emitter_ldr.py)
+int iris_tri_accumulate(const int32_t *prim, const uint8_t *valid, const float *radiance, int64_t n, int64_t n_faces, float *tri_sum, int32_t *tri_count,
+                        void *stream) {
+    if (n < 0 || n_faces < 0) return fail(IRIS_ERR_INVALID, "bad tri_accumulate arguments");
+    if (n == 0) return IRIS_OK;
+    if (!prim || !radiance || !tri_sum || !tri_count) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_tri_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prim, valid, radiance, n, n_faces, tri_sum, tri_count);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_emitter_classify(const float *tri_sum, const int32_t *tri_count, int64_t n_faces, float threshold, uint8_t *is_emitter, void *stream) {
+    if (n_faces < 0) return fail(IRIS_ERR_INVALID, "n_faces < 0");
+    if (n_faces == 0) return IRIS_OK;
+    if (!tri_sum || !tri_count || !is_emitter) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_emitter_classify<<<(unsigned)((n_faces + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tri_sum, tri_count, n_faces, threshold, is_emitter);
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+int iris_emitter_geometry(const float *verts, const int32_t *faces, const int64_t *emitter_faces, int64_t n_emitters, float *out_vertices, float *out_area,
+                          float *out_normal, void *stream) {
+    if (n_emitters < 0) return fail(IRIS_ERR_INVALID, "n_emitters < 0");
+    if (n_emitters == 0) return IRIS_OK;
+    if (!verts || !faces || !emitter_faces || !out_vertices || !out_area || !out_normal) return fail(IRIS_ERR_INVALID, "NULL array");
+    k_emitter_geometry<<<(unsigned)((n_emitters + 127) / 128), 128, 0, (cudaStream_t)stream>>>(verts, faces, emitter_faces, n_emitters, out_vertices, out_area, out_normal);
     LAUNCHED();
     return IRIS_OK;
 }

@@ -739,3 +739,38 @@ def test_slf_bake_on_device_matches_reference_golden(small):
     bk2.observe_bounds(torch.zeros(0, 3, device=dev))
     lo, hi = bk2.observed_bounds()
     assert lo == float(views[0][0].min()) and hi == float(views[0][0].max())
+
+
+@pytest.mark.gpu
+def test_emitter_extraction_on_device_matches_oracle(small):
+    """extract_emitter_ldr.py:76-110 on the device: ray_intersect's triangle indices + LDR radiance -> per-triangle mean ->
+    is_emitter / vertices / area / normal, against the torch restatement (is_emitter and vertices exact, area / normal 1e-6)."""
+    from iris_b200 import core
+    from iris_b200.emitter_extract import EmitterExtractor
+    from oracle import emitter_extract as OE
+    dev, sc = small["dev"], small["sc"]
+    V, F = torch.as_tensor(sc.vertices), torch.as_tensor(sc.faces).long()
+    lit = (torch.arange(len(F)) % 7) == 0                      # the triangles whose pixels are saturated in the synthetic LDR images
+    g = torch.Generator().manual_seed(8)
+    views = []
+    ex = EmitterExtractor(len(F), dev)
+    for view in (1, 2, 3):
+        rays = torch.as_tensor(sc.camera_rays(96, 72, view=view))
+        t, prim, uv, p, n = small["scene"].intersect_raw(rays[:, 0:3].contiguous().to(dev), rays[:, 3:6].contiguous().to(dev))
+        idx = prim.long().cpu()
+        valid = idx >= 0
+        rgb = torch.rand(len(idx), 3, generator=g) * 0.6                                   # LDR image: lit triangles saturate
+        rgb[valid & lit[idx.clamp_min(0)]] = 1.0
+        views.append((idx, valid, rgb))
+        ex.accumulate(prim, valid.to(dev), rgb.to(dev))
+    want = OE.extract(views, V, F, 0.99)
+    got = ex.finalize(V, F, 0.99)
+    assert int(want["is_emitter"].sum()) > 0
+    assert torch.equal(got["is_emitter"].cpu(), want["is_emitter"])
+    assert torch.equal(ex.tri_count.cpu().float(), want["triangle_count"])
+    assert torch.equal(got["emitter_vertices"].cpu(), want["emitter_vertices"])
+    assert torch.allclose(got["emitter_area"].cpu(), want["emitter_area"], rtol=1e-6, atol=0) and torch.allclose(got["emitter_normal"].cpu(), want["emitter_normal"], rtol=1e-6, atol=1e-7)
+    assert got["emitter_radiance"].shape == (len(F), 3)
+    # the dict loads into the estimator tables like an emitter.pth
+    T = core.ShadingTables(dev).set_emitter(got["is_emitter"], got["emitter_vertices"], got["emitter_area"], torch.zeros(len(F), 3, device=dev))
+    assert T.K == int(want["is_emitter"].sum())

@@ -180,3 +180,15 @@ def test_slf_bake_oracle_matches_reference_golden():
     assert np.array_equal(np.packbits(out["mask"].numpy().reshape(-1)), g["mask"])
     assert np.array_equal(out["weight"]["inds"].numpy(), g["inds"]) and np.array_equal(out["weight"]["count"].numpy(), g["count"])
     assert np.array_equal(out["weight"]["radiance"].numpy(), g["radiance"])
+
+
+def test_emitter_extract_oracle_basic():
+    """oracle/emitter_extract.py (extract_emitter_ldr.py:76-110): a saturated triangle becomes an emitter with the right geometry."""
+    import torch
+    from oracle import emitter_extract as OE
+    V = torch.tensor([[0., 0., 0.], [2., 0., 0.], [0., 2., 0.], [0., 0., 1.]])
+    F = torch.tensor([[0, 1, 2], [0, 1, 3]])
+    views = [(torch.tensor([0, 0, 1, -1]), torch.tensor([True, True, True, False]), torch.tensor([[1., 1., 1.], [1., .98, 1.], [.2, .3, .1], [9., 9., 9.]]))]
+    out = OE.extract(views, V, F, 0.9)
+    assert out["is_emitter"].tolist() == [True, False] and out["triangle_count"].tolist() == [2.0, 1.0]
+    assert torch.allclose(out["emitter_area"], torch.tensor([2.0])) and torch.allclose(out["emitter_normal"], torch.tensor([[0., 0., 1.]]))
