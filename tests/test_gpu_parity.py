@@ -774,3 +774,31 @@ def test_emitter_extraction_on_device_matches_oracle(small):
     # the dict loads into the estimator tables like an emitter.pth
     T = core.ShadingTables(dev).set_emitter(got["is_emitter"], got["emitter_vertices"], got["emitter_area"], torch.zeros(len(F), 3, device=dev))
     assert T.K == int(want["is_emitter"].sum())
+
+
+@pytest.mark.gpu
+def test_c_abi_error_convention(small):
+    """Bad calls return a negative status and leave a message in iris_last_error(); they never launch work (include/iris_b200.h)."""
+    import ctypes
+    from iris_b200 import core
+    C = core.C
+    lib = C.lib()
+    dev = small["dev"]
+    o = torch.zeros(4, 3, device=dev)
+    out = torch.zeros(4, device=dev)
+    l0 = lib.iris_launch_count()
+    assert lib.iris_intersect(None, C.ptr(o), C.ptr(o), 4, C.ptr(out), None, None, None, None, None) == -1 and b"scene" in lib.iris_last_error()
+    assert lib.iris_intersect(small["scene"].handle, None, None, 4, C.ptr(out), None, None, None, None, None) == -1
+    assert lib.iris_intersect(small["scene"].handle, C.ptr(o), C.ptr(o), -1, C.ptr(out), None, None, None, None, None) == -1
+    P, S = small["tables"].c(), core.Sampler(seed=1).c()
+    rays = torch.as_tensor(small["rays"][:8]).to(dev)
+    L = torch.zeros(8, 3, device=dev)
+    ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+    rc = lib.iris_single_forward(small["scene"].handle, ctypes.byref(P), C.ptr(rays), 8, 4, ctypes.byref(S), C.ptr(L), None, C.ptr(ws), ws.numel(), None)
+    assert rc == -4 and b"workspace" in lib.iris_last_error()
+    assert lib.iris_brdf_shading_forward(C.ptr(L), C.ptr(L), C.ptr(L), C.ptr(L), 1, 8, C.ptr(L), None) == -1          # n_levels < 2
+    assert lib.iris_slf_mark(C.ptr(o), None, 4, 0.0, 0.0, 32, C.ptr(out), None) == -1                                   # empty voxel range
+    assert lib.iris_set_option(b"no_such_option", 1) != 0
+    assert lib.iris_launch_count() == l0
+    with pytest.raises(RuntimeError, match="scene is NULL"):                                                               # the Python layer raises
+        C.check(lib.iris_intersect(None, C.ptr(o), C.ptr(o), 4, C.ptr(out), None, None, None, None, None))
