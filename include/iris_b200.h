@@ -133,10 +133,12 @@ int iris_bake(const IrisScene *scene, const IrisShadeParams *params, int mode, f
  * ---------------------------------------------------------------------------------------------- */
 /* Hash-grid level table (32 entries each): returns the total number of grid entries (13 977 056). */
 int64_t iris_field_levels(float *scale, uint32_t *res, uint32_t *size, uint32_t *offset);
-int iris_field_forward(const IrisShadeParams *params, const float *position, int64_t n, float *mat, void *stream);
+/* encoded (optional, may be NULL): n x 64 fp16 = 128 bytes per sample, 16-byte aligned.  The forward stores each sample's hash-grid
+ * features there; a backward given the same array reads them instead of gathering the grid a second time. */
+int iris_field_forward(const IrisShadeParams *params, const float *position, int64_t n, float *mat, void *encoded, void *stream);
 int64_t iris_field_backward_workspace_bytes(int64_t n);
 int iris_field_backward(const IrisShadeParams *params, const float *position, const float *d_mat, int64_t n,
-                        float *d_params, void *workspace, int64_t workspace_bytes, void *stream);
+                        float *d_params, const void *encoded, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * path_tracing_single forward + adjoint (utils/path_tracing.py:320-407), the estimator

@@ -43,9 +43,9 @@ PROTOTYPES = {
     "iris_bake": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_i64, c_i32,
                                  ctypes.POINTER(IrisSampler), c_vp, c_vp, c_vp]),
     "iris_field_levels": (c_i64, [c_vp, c_vp, c_vp, c_vp]),
-    "iris_field_forward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_vp, c_vp]),
+    "iris_field_forward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_vp, c_vp, c_vp]),
     "iris_field_backward_workspace_bytes": (c_i64, [c_i64]),
-    "iris_field_backward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "iris_field_backward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_single_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "iris_single_record_bytes": (c_i64, [c_i64, c_i32]),
     "iris_single_forward": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_i32, ctypes.POINTER(IrisSampler),

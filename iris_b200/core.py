@@ -199,17 +199,19 @@ def bake(scene, tables, mode, roughness, position, normal, wo, spp, sampler):
     return out0 if mode == 0 else (out0, out1)
 
 
-def field_forward(tables, position):
+def field_forward(tables, position, want_encoded=False):
+    """NGPBRDF.forward: mat (n,5).  want_encoded: also return the (n,64) fp16 hash-grid features for field_backward(encoded=...)."""
     position = position.contiguous().float()
     n = position.shape[0]
     mat = torch.empty(n, 5, device=position.device)
+    enc = torch.empty(n, 64, dtype=torch.float16, device=position.device) if want_encoded else None
     P = tables.c()
     with torch.cuda.device(position.device):
-        C.check(C.lib().iris_field_forward(ctypes.byref(P), C.ptr(position), n, C.ptr(mat), C.stream_ptr()))
-    return mat
+        C.check(C.lib().iris_field_forward(ctypes.byref(P), C.ptr(position), n, C.ptr(mat), C.ptr(enc), C.stream_ptr()))
+    return (mat, enc) if want_encoded else mat
 
 
-def field_backward(tables, position, d_mat, d_params=None, workspace=None):
+def field_backward(tables, position, d_mat, d_params=None, workspace=None, encoded=None):
     """Adjoint of NGPBRDF.forward: accumulates into d_params (flat fp32 [mlp 9216 | grid], tcnn layout) and returns it."""
     position = position.contiguous().float()
     d_mat = d_mat.contiguous().float()
@@ -223,7 +225,8 @@ def field_backward(tables, position, d_mat, d_params=None, workspace=None):
         workspace = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
     P = tables.c()
     with torch.cuda.device(dev):
-        C.check(lib.iris_field_backward(ctypes.byref(P), C.ptr(position), C.ptr(d_mat), n, C.ptr(d_params), C.ptr(workspace), workspace.numel(), C.stream_ptr()))
+        C.check(lib.iris_field_backward(ctypes.byref(P), C.ptr(position), C.ptr(d_mat), n, C.ptr(d_params), C.ptr(encoded), C.ptr(workspace), workspace.numel(),
+                                        C.stream_ptr()))
     return d_params
 
 

@@ -491,7 +491,7 @@ static int launch_field(const IrisShadeParams *P, int64_t n, const float *positi
     return IRIS_OK;
 }
 
-int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t n, float *mat, void *stream) {
+int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t n, float *mat, void *encoded, void *stream) {
     if (!P || !P->grid_f16 || !P->mlp_f16 || !(P->field_range > 0.f)) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
     if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
     if (n == 0) return IRIS_OK;
@@ -500,7 +500,8 @@ int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t 
     CUDA_TRY(cudaGetDevice(&dev));
     int rc = ensure_device_setup(dev);
     if (rc) return rc;
-    return launch_field(P, n, position, mat, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    if (reinterpret_cast<uintptr_t>(encoded) & 15) return fail(IRIS_ERR_INVALID, "encoded must be 16-byte aligned");
+    return launch_field(P, n, position, mat, nullptr, nullptr, nullptr, (cudaStream_t)stream, reinterpret_cast<__half *>(encoded));
 }
 
 #ifndef FIELD_BWD_CHUNK_LOG2
@@ -549,8 +550,8 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
 
 int64_t iris_field_backward_workspace_bytes(int64_t n) { return std::min<int64_t>(std::max<int64_t>(n, 1), FIELD_BWD_CHUNK) * FIELD_ACT_BYTES_PER_SAMPLE; }
 
-int iris_field_backward(const IrisShadeParams *P, const float *position, const float *d_mat, int64_t n, float *d_params, void *workspace,
-                        int64_t workspace_bytes, void *stream) {
+int iris_field_backward(const IrisShadeParams *P, const float *position, const float *d_mat, int64_t n, float *d_params, const void *encoded,
+                        void *workspace, int64_t workspace_bytes, void *stream) {
     if (!P || !P->grid_f16 || !P->mlp_f16 || !(P->field_range > 0.f)) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
     if (n < 0) return fail(IRIS_ERR_INVALID, "n < 0");
     if (n == 0) return IRIS_OK;
@@ -560,7 +561,9 @@ int iris_field_backward(const IrisShadeParams *P, const float *position, const f
     CUDA_TRY(cudaGetDevice(&dev));
     int rc = ensure_device_setup(dev);
     if (rc) return rc;
-    return run_field_backward(P, n, position, nullptr, d_mat, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (reinterpret_cast<uintptr_t>(encoded) & 15) return fail(IRIS_ERR_INVALID, "encoded must be 16-byte aligned");
+    return run_field_backward(P, n, position, nullptr, d_mat, d_params, workspace, workspace_bytes, (cudaStream_t)stream,
+                              reinterpret_cast<__half *>(const_cast<void *>(encoded)));
 }
 
 int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {

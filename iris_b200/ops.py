@@ -176,15 +176,19 @@ class FieldForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, params, tables, position):
         ctx.tables = tables
-        ctx.save_for_backward(position)
         ctx.n_params = params.numel()
+        if params.requires_grad:
+            mat, enc = core.field_forward(tables, position, want_encoded=True)      # the adjoint reuses the encoded inputs
+            ctx.save_for_backward(position, enc)
+            return mat
+        ctx.save_for_backward(position, None)
         return core.field_forward(tables, position)
 
     @staticmethod
     def backward(ctx, d_mat):
-        (position,) = ctx.saved_tensors
+        position, enc = ctx.saved_tensors
         d = torch.zeros(ctx.n_params, device=d_mat.device, dtype=torch.float32)
-        core.field_backward(ctx.tables, position, d_mat, d)
+        core.field_backward(ctx.tables, position, d_mat, d, encoded=enc)
         return d, None, None
 
 
@@ -216,20 +220,20 @@ class BrdfShading(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, params, tables, position, diffuse, specular0, specular1):
-        mat = core.field_forward(tables, position)
+        mat, enc = core.field_forward(tables, position, want_encoded=True)
         L = core.brdf_shading_forward(mat, diffuse, specular0, specular1)
         ctx.tables = tables
         ctx.n_params = params.numel()
-        ctx.save_for_backward(position, mat, diffuse, specular0, specular1)
+        ctx.save_for_backward(position, mat, diffuse, specular0, specular1, enc)
         return L, mat
 
     @staticmethod
     def backward(ctx, dL, d_mat_up):
-        position, mat, diffuse, specular0, specular1 = ctx.saved_tensors
+        position, mat, diffuse, specular0, specular1, enc = ctx.saved_tensors
         d_mat = d_mat_up.contiguous().float().clone() if d_mat_up is not None else None
         d_mat = core.brdf_shading_backward(mat, diffuse, specular0, specular1, dL, d_mat)
         d = torch.zeros(ctx.n_params, device=dL.device, dtype=torch.float32)
-        core.field_backward(ctx.tables, position, d_mat, d)
+        core.field_backward(ctx.tables, position, d_mat, d, encoded=enc)
         return d, None, None, None, None, None
 
 

@@ -277,6 +277,11 @@ def test_field_backward_matches_oracle(small):
         assert err < 2e-3, (name, err)
     nz = np.nonzero(ref[9216:])[0]
     assert np.array_equal(np.nonzero(got[9216:])[0], nz) or len(np.setxor1d(np.nonzero(got[9216:])[0], nz)) < 1e-3 * len(nz)
+    # the same adjoint from the encoded inputs kept by the forward (no second gather of the grid): same result up to atomics order
+    mat, enc = core.field_forward(small["tables"], x.to(small["dev"]), want_encoded=True)
+    assert enc.shape == (n, 64) and enc.dtype == torch.float16 and torch.equal(mat, core.field_forward(small["tables"], x.to(small["dev"])))
+    got2 = core.field_backward(small["tables"], x.to(small["dev"]), dmat.to(small["dev"]), encoded=enc).cpu().numpy()
+    assert np.allclose(got2, got, rtol=1e-4, atol=1e-6 * np.abs(got).max())
 
 
 @pytest.mark.parametrize("name", ["small", "c1"])
