@@ -146,9 +146,11 @@ int iris_field_backward(const IrisShadeParams *params, const float *position, co
  *   rays: (B,12) = o,d,dxdu,dydv (utils/dataset/synthetic_ldr.py:50-57); L (B,3) = mean over spp.
  *   Sampler columns: 0 du,1 dv,2 e1,3 e2x,4 e2y,5 b1,6 b2x,7 b2y.
  *   record: NULL for inference; otherwise >= iris_single_record_bytes(B,spp) bytes that the adjoint
- *   replays (per sample: emitter rows + coefficients of the three radiance gathers, and the 3x3
- *   sparse Jacobian of the sample's radiance wrt albedo/roughness/metallic).
- *   workspace: >= iris_single_workspace_bytes(B,spp).
+ *   replays (per sample 96 bytes: emitter rows + coefficients of the three radiance gathers, the 3x3
+ *   sparse Jacobian of the sample's radiance wrt albedo/roughness/metallic, the hit point; plus the
+ *   128 bytes of encoded field inputs the field adjoint reads instead of gathering the grid again).
+ *   workspace: >= iris_single_workspace_bytes(B,spp): three 16-byte words per sample and the ray queue
+ *   of one chunk (the secondary bounce runs as generate -> persistent ray-queue trace -> shade).
  * iris_single_backward: dL (B,3) -> d_radiance (K,3) accumulated; d_mat (B*spp,5) written (feed it,
  * with `x0` = the primary hit positions held in the record, to iris_field_backward via
  * iris_single_backward's d_params argument: when d_params != NULL the field adjoint is run too).
