@@ -87,7 +87,7 @@ __device__ __forceinline__ void field_level_weights(const FieldLevel &L, f3 x, f
 }
 
 template <int DENSE_L>
-__device__ __forceinline__ void field_level_gather(const __half2 *__restrict__ grid, f3 x, int l, __half2 v[8]) {
+__device__ __forceinline__ void field_level_gather(const __half2 *__restrict__ grid, f3 x, int l, __half2 v[8], bool pair = true) {
     const FieldLevel L = c_levels[l];
     uint32_t idx[8];
     float w[8];
@@ -95,9 +95,11 @@ __device__ __forceinline__ void field_level_gather(const __half2 *__restrict__ g
     // volatile asm keeps the gathers of a whole group in program order ahead of their consumers (ptxas otherwise sinks every load
     // next to its use to save registers, leaving one or two requests in flight per lane)
 #ifndef FIELD_GATHER_NO_V2
-    if (DENSE_L < 0 && (idx[0] ^ idx[1]) == 1u) {
+    if (DENSE_L < 0 && pair && (idx[0] ^ idx[1]) == 1u) {
         // hashed level, even cell x: corners c and c+1 (x, x+1 at the same y, z) hash to idx and idx ^ 1, the two halves of one aligned
-        // 8-byte slot -> four 8-byte loads instead of eight 4-byte ones (same sectors, half the L1 requests)
+        // 8-byte slot -> four 8-byte loads instead of eight 4-byte ones (same sectors, half the L1 requests).  `pair` is a launch-uniform
+        // switch: +20 % on incoherent positions (secondary hits, training pixels), -1.5 % on the spp-coherent primary hits of
+        // path_tracing_single, whose lanes mostly share sectors anyway -- that caller turns it off
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
             uint32_t r0, r1;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void field_level_reduce(f3 x, int l, const __half2 v[
 // The gathers of a GROUP of levels (4 dense, or 5 hashed: 32-40 independent 4-byte loads) are issued before anything is consumed,
 // so each lane keeps dozens of L2 requests in flight -- the encoder is latency-bound, not bandwidth-bound.
 template <class Put>
-__device__ __forceinline__ void field_encode_to(const __half2 *__restrict__ grid, f3 x, Put put) {
+__device__ __forceinline__ void field_encode_to(const __half2 *__restrict__ grid, f3 x, Put put, bool pair = true) {
     const uint32_t zero = c_levels[0].dense - 1u;      // 0 at run time (level 0 is dense), opaque to the compiler
     {
         __half2 v[4][8];
@@ -178,15 +180,15 @@ __device__ __forceinline__ void field_encode_to(const __half2 *__restrict__ grid
     for (int l0 = FIELD_DENSE_LEVELS; l0 < FIELD_LEVELS; l0 += 5) {
         __half2 v[5][8];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) field_level_gather<-1>(grid, x, l0 + k, v[k]);
+        for (int k = 0; k < 5; ++k) field_level_gather<-1>(grid, x, l0 + k, v[k], pair);
         field_pin_group<5>(v, zero);
 #pragma unroll
         for (int k = 0; k < 5; ++k) field_level_reduce(x, l0 + k, v[k], put);
     }
 }
 // ... to a contiguous row dst[0..63]
-__device__ __forceinline__ void field_encode(const __half2 *__restrict__ grid, f3 x, __half *dst) {
-    field_encode_to(grid, x, [dst](int l, __half2 v) { *reinterpret_cast<__half2 *>(dst + 2 * l) = v; });
+__device__ __forceinline__ void field_encode(const __half2 *__restrict__ grid, f3 x, __half *dst, bool pair = true) {
+    field_encode_to(grid, x, [dst](int l, __half2 v) { *reinterpret_cast<__half2 *>(dst + 2 * l) = v; }, pair);
 }
 
 __device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], const uint32_t b[2]) {
@@ -265,7 +267,7 @@ __device__ __forceinline__ void warp_tile_to_global(const __half *Xs, __half *ds
 template <bool WS>
 __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P, int64_t n, const float *__restrict__ position, float *__restrict__ mat,
                                                                const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2,
-                                                               __half *__restrict__ x_save) {
+                                                               __half *__restrict__ x_save, int pair) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half *Wsm = reinterpret_cast<__half *>(smem_raw);
     __half *Xs = Wsm + (64 + 64 + 16) * FIELD_LD + (threadIdx.x >> 5) * 32 * FIELD_LD;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P,
         if (active) {
             const f3 x = mk3(field_coord(p.x, P.field_vmin, P.field_range), field_coord(p.y, P.field_vmin, P.field_range),
                              field_coord(p.z, P.field_vmin, P.field_range));
-            field_encode(reinterpret_cast<const __half2 *>(P.grid_f16), x, row);
+            field_encode(reinterpret_cast<const __half2 *>(P.grid_f16), x, row, pair != 0);
         } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k) *reinterpret_cast<__half2 *>(row + 2 * k) = __floats2half2_rn(0.f, 0.f);

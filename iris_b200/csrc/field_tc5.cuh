@@ -62,7 +62,7 @@ __device__ int g_tc5_debug = 0;   // 0 normal, 1 skip the encode, 2 skip the MLP
 template <bool WS>
 __global__ void __launch_bounds__(TC5_ROWS) k_field_forward_tc5(IrisShadeParams P, int64_t n, const float *__restrict__ position, float *__restrict__ mat,
                                                                  const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2,
-                                                                 __half *__restrict__ x_save) {
+                                                                 __half *__restrict__ x_save, int pair) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sA = smem_raw;
     unsigned char *sW1 = sA + TC5_A_BYTES, *sW2 = sW1 + 8192, *sW3 = sW2 + 8192;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(TC5_ROWS) k_field_forward_tc5(IrisShadeParams 
             const f3 x = mk3(field_coord(p.x, P.field_vmin, P.field_range), field_coord(p.y, P.field_vmin, P.field_range),
                              field_coord(p.z, P.field_vmin, P.field_range));
             unsigned char *rowp = sA + row_off;
-            field_encode_to(grid, x, [rowp](int l, __half2 v) { *reinterpret_cast<__half2 *>(rowp + (l >> 2) * TC5_A_LBO + (l & 3) * 4) = v; });
+            field_encode_to(grid, x, [rowp](int l, __half2 v) { *reinterpret_cast<__half2 *>(rowp + (l >> 2) * TC5_A_LBO + (l & 3) * 4) = v; }, pair != 0);
         } else {
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4 *>(sA + kc * TC5_A_LBO + row_off) = make_uint4(0, 0, 0, 0);

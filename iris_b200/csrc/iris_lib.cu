@@ -460,7 +460,7 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
 }
 
 static int launch_field(const IrisShadeParams *P, int64_t n, const float *position, float *mat, const float4 *w0, float4 *w1, float4 *w2, cudaStream_t st,
-                        __half *x_save = nullptr) {
+                        __half *x_save = nullptr, int pair = 1) {
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
@@ -481,11 +481,11 @@ static int launch_field(const IrisShadeParams *P, int64_t n, const float *positi
     ProfScope ps(K_FIELD_FORWARD, st);
     if (g_field_impl == 1) {
         const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * g_tc5_ctas);
-        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
-        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
+        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
+        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
     } else {
-        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
-        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save);
+        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
+        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
     }
     LAUNCHED();
     return IRIS_OK;
@@ -595,7 +595,8 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         k_primary<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1);
     }
     LAUNCHED();
-    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st, record ? reinterpret_cast<__half *>(reinterpret_cast<float4 *>(record) + 6 * n) : nullptr);
+    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st, record ? reinterpret_cast<__half *>(reinterpret_cast<float4 *>(record) + 6 * n) : nullptr,
+                      /*pair=*/0);          // primary hits: the spp samples of a pixel share sectors, paired gathers do not pay
     if (rc) return rc;
     if (g_single_impl == 0) {
         ProfScope ps(K_BOUNCE_SINGLE, st);
