@@ -298,7 +298,7 @@ def main():
     n_chunks = w["SPP"] // w["spp"]
     pix_per_view = w["width"] * w["height"]
     config = dict(workload=a.workload, description=w["desc"], triangles=None, views_per_gpu=w["views"], width=w["width"], height=w["height"],
-                  SPP=w["SPP"], spp=w["spp"], emitters=w["emitters"], slf_H=256, sharding="pixels by view, scene/SLF/field replicated, allreduce(d_radiance)",
+                  SPP=w["SPP"], spp=w["spp"], emitters=w["emitters"], slf_H=256, sharding="weak scaling: N x views_per_gpu views in total, each rank takes pixel band rank/N of every view (all spp of a pixel on one rank); scene/SLF/field replicated; one allreduce of the gradient buffer per step",
                   l2="inputs larger than L2 (BVH+triangles 62 MB, SLF 64 MB+, hash grid 56 MB, per-tile records > 400 MB)")
 
     if a.impl == "reference":
@@ -339,8 +339,16 @@ def main():
         lo_v, hi_v = idist.shard_range(w["views"], rank, world)
         views = [v + 1 for v in range(lo_v, hi_v)]
     else:
-        views = [rank * w["views"] + v + 1 for v in range(w["views"])]
-    rays_host = torch.cat([torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=v)) for v in views]).pin_memory()
+        views = [v + 1 for v in range(world * w["views"])]   # weak scaling: world x views in total ...
+    per_view = []
+    for v in views:
+        r = torch.as_tensor(sc.camera_rays(w["width"], w["height"], view=v))
+        if not w.get("strong") and world > 1:                # ... and every rank takes the same pixel band of EVERY view, so that the
+            lo_p, hi_p = idist.shard_range(r.shape[0], rank, world)   # ranks' work is balanced whatever the views cost
+            r = r[lo_p:hi_p].clone()
+        per_view.append(r)
+    rays_host = torch.cat(per_view).pin_memory()
+    del per_view
     rays_dev = rays_host.to(dev)
     P = rays_host.shape[0]
     spp = w["spp"]
