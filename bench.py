@@ -356,6 +356,9 @@ def main():
     lib = core.C.lib()
     ws = torch.empty(lib.iris_single_workspace_bytes(tile, spp), dtype=torch.uint8, device=dev)   # forward streams | d_mat + activation streams
     recs = [torch.empty(lib.iris_single_record_bytes(tile, spp), dtype=torch.uint8, device=dev) for _ in range(n_chunks)]
+    want_par = bool(w.get("brdf_grad"))
+    # encoded field inputs of every sample, kept from forward to adjoint only when the field gradient is wanted
+    encs = [torch.empty(lib.iris_single_encoded_bytes(tile, spp), dtype=torch.uint8, device=dev) if want_par else None for _ in range(n_chunks)]
     target = torch.full((P, 3), 0.5, device=dev)
     n_samples_rank = P * w["SPP"]
     step_no = [0]
@@ -380,7 +383,7 @@ def main():
                 Lc = torch.empty(t1 - t0, 3, device=dev)
                 P_, S_ = tables.c(), smp.c()
                 core.C.check(lib.iris_single_forward(scene.handle, P_, core.C.ptr(rays), t1 - t0, spp, S_, core.C.ptr(Lc), core.C.ptr(recs[c]),
-                                                     core.C.ptr(ws), ws.numel(), core.C.stream_ptr()))
+                                                     core.C.ptr(encs[c]), core.C.ptr(ws), ws.numel(), core.C.stream_ptr()))
                 L += Lc
             L /= n_chunks
             diff = L - target[t0:t1]
@@ -388,7 +391,7 @@ def main():
             dL = diff * (2.0 / (P * 3 * world * n_chunks))
             for c in range(n_chunks):
                 P_ = tables.c()
-                core.C.check(lib.iris_single_backward(P_, core.C.ptr(dL), t1 - t0, spp, core.C.ptr(recs[c]), core.C.ptr(d_rad), core.C.ptr(d_par_buf),
+                core.C.check(lib.iris_single_backward(P_, core.C.ptr(dL), t1 - t0, spp, core.C.ptr(recs[c]), core.C.ptr(encs[c]), core.C.ptr(d_rad), core.C.ptr(d_par_buf),
                                                       core.C.ptr(ws) if want_par else None, ws.numel() if want_par else 0, core.C.stream_ptr()))
         if dist is not None:
             idist.allreduce_gradients([d_rad, d_par_buf])

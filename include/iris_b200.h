@@ -147,8 +147,11 @@ int iris_field_backward(const IrisShadeParams *params, const float *position, co
  *   Sampler columns: 0 du,1 dv,2 e1,3 e2x,4 e2y,5 b1,6 b2x,7 b2y.
  *   record: NULL for inference; otherwise >= iris_single_record_bytes(B,spp) bytes that the adjoint
  *   replays (per sample 96 bytes: emitter rows + coefficients of the three radiance gathers, the 3x3
- *   sparse Jacobian of the sample's radiance wrt albedo/roughness/metallic, the hit point; plus the
- *   128 bytes of encoded field inputs the field adjoint reads instead of gathering the grid again).
+ *   sparse Jacobian of the sample's radiance wrt albedo/roughness/metallic, the hit point).
+ *   encoded: optional (NULL, or >= iris_single_encoded_bytes(B,spp) = 128 bytes per sample, 16-byte aligned): the forward keeps
+ *   every sample's 64 fp16 hash-grid features there; a backward with d_params != NULL that is given the same array reads them
+ *   instead of gathering the grid a second time (without it the adjoint re-encodes from the hit points in the record).  Pass
+ *   NULL when only the emitter gradient is wanted (train_emitter.py).
  *   workspace: >= iris_single_workspace_bytes(B,spp): three 16-byte words per sample and the ray queue
  *   of one chunk (the secondary bounce runs as generate -> persistent ray-queue trace -> shade).
  * iris_single_backward: dL (B,3) -> d_radiance (K,3) accumulated; d_mat (B*spp,5) written (feed it,
@@ -157,11 +160,12 @@ int iris_field_backward(const IrisShadeParams *params, const float *position, co
  * ---------------------------------------------------------------------------------------------- */
 int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp);
 int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp);
+int64_t iris_single_encoded_bytes(int64_t n_pixels, int32_t spp);
 int iris_single_forward(const IrisScene *scene, const IrisShadeParams *params, const float *rays,
                         int64_t n_pixels, int32_t spp, const IrisSampler *sampler, float *L,
-                        void *record, void *workspace, int64_t workspace_bytes, void *stream);
+                        void *record, void *encoded, void *workspace, int64_t workspace_bytes, void *stream);
 int iris_single_backward(const IrisShadeParams *params, const float *dL, int64_t n_pixels, int32_t spp,
-                         const void *record, float *d_radiance, float *d_params,
+                         const void *record, const void *encoded, float *d_radiance, float *d_params,
                          void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------

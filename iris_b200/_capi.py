@@ -48,9 +48,10 @@ PROTOTYPES = {
     "iris_field_backward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_single_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "iris_single_record_bytes": (c_i64, [c_i64, c_i32]),
+    "iris_single_encoded_bytes": (c_i64, [c_i64, c_i32]),
     "iris_single_forward": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_i32, ctypes.POINTER(IrisSampler),
-                                           c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "iris_single_backward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+                                           c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "iris_single_backward": (ctypes.c_int, [ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "iris_wave_workspace_bytes": (c_i64, [c_i64]),
     "iris_path_tracing": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), c_vp, c_i64, c_i32, c_i32, ctypes.POINTER(IrisSampler), c_vp, c_vp, c_i64, c_vp]),
     "iris_path_tracing_det": (ctypes.c_int, [c_vp, ctypes.POINTER(IrisShadeParams), ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32,

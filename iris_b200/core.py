@@ -256,8 +256,9 @@ def brdf_shading_backward(mat, diffuse, specular0, specular1, dL, d_mat=None):
     return d_mat
 
 
-def single_forward(scene, tables, rays, spp, sampler, want_record=False, workspace=None):
-    """path_tracing_single forward.  Returns (L (B,3), record or None)."""
+def single_forward(scene, tables, rays, spp, sampler, want_record=False, workspace=None, want_encoded=None):
+    """path_tracing_single forward.  Returns (L (B,3), record or None).  want_encoded (default: same as want_record): also keep the
+    samples' encoded field inputs for the field adjoint; they travel with the record as `record.encoded`."""
     rays = rays.contiguous().float()
     B = rays.shape[0]
     dev = rays.device
@@ -267,10 +268,15 @@ def single_forward(scene, tables, rays, spp, sampler, want_record=False, workspa
     if workspace is None or workspace.numel() < wb:
         workspace = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
     record = torch.empty(max(lib.iris_single_record_bytes(B, int(spp)), 16), dtype=torch.uint8, device=dev) if want_record else None
+    if want_encoded is None:
+        want_encoded = want_record
+    enc = torch.empty(max(lib.iris_single_encoded_bytes(B, int(spp)), 16), dtype=torch.uint8, device=dev) if (want_record and want_encoded) else None
     P, S = tables.c(), sampler.c()
     with torch.cuda.device(dev):
-        C.check(lib.iris_single_forward(scene.handle, ctypes.byref(P), C.ptr(rays), B, int(spp), ctypes.byref(S), C.ptr(L), C.ptr(record),
+        C.check(lib.iris_single_forward(scene.handle, ctypes.byref(P), C.ptr(rays), B, int(spp), ctypes.byref(S), C.ptr(L), C.ptr(record), C.ptr(enc),
                                         C.ptr(workspace), workspace.numel(), C.stream_ptr()))
+    if record is not None:
+        record.encoded = enc
     return L, record
 
 
@@ -286,7 +292,7 @@ def single_backward(tables, dL, spp, record, want_radiance=True, d_params=None, 
         workspace = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
     P = tables.c()
     with torch.cuda.device(dev):
-        C.check(lib.iris_single_backward(ctypes.byref(P), C.ptr(dL), B, int(spp), C.ptr(record), C.ptr(d_rad), C.ptr(d_params),
+        C.check(lib.iris_single_backward(ctypes.byref(P), C.ptr(dL), B, int(spp), C.ptr(record), C.ptr(getattr(record, "encoded", None)), C.ptr(d_rad), C.ptr(d_params),
                                          C.ptr(workspace), 0 if workspace is None else workspace.numel(), C.stream_ptr()))
     return d_rad
 

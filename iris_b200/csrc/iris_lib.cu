@@ -572,11 +572,12 @@ int64_t iris_single_workspace_bytes(int64_t n_pixels, int32_t spp) {
     const int64_t bwd = ((5 * 4 * n + 15) / 16) * 16 + iris_field_backward_workspace_bytes(n);   // d_mat | activation streams of one chunk
     return std::max(fwd, bwd);
 }
-// per sample: 6 float4 of estimator record + the 64 fp16 encoded field inputs (read back by the field adjoint instead of re-gathering)
-int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp) { return (6 * 16 + 128) * n_pixels * (int64_t)spp; }
+// per sample: 6 float4 of estimator record; separately (optional) the 64 fp16 encoded field inputs the field adjoint reads back
+int64_t iris_single_record_bytes(int64_t n_pixels, int32_t spp) { return 6 * 16 * n_pixels * (int64_t)spp; }
+int64_t iris_single_encoded_bytes(int64_t n_pixels, int32_t spp) { return 128 * n_pixels * (int64_t)spp; }
 
 int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const float *rays, int64_t n_pixels, int32_t spp, const IrisSampler *sampler,
-                        float *L, void *record, void *workspace, int64_t workspace_bytes, void *stream) {
+                        float *L, void *record, void *encoded, void *workspace, int64_t workspace_bytes, void *stream) {
     if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
     int rc = check_params(P, true);
     if (rc) return rc;
@@ -585,7 +586,8 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
     if (!rays || !L || !workspace) return fail(IRIS_ERR_INVALID, "NULL array");
     if (sampler->U && sampler->stride < 8) return fail(IRIS_ERR_INVALID, "sampler stride < 8");
     if (workspace_bytes < iris_single_workspace_bytes(n_pixels, spp)) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
-    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(record) & 15)) return fail(IRIS_ERR_INVALID, "workspace/record must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(record) & 15) || (reinterpret_cast<uintptr_t>(encoded) & 15))
+        return fail(IRIS_ERR_INVALID, "workspace/record/encoded must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = n_pixels * spp;
     float4 *w0 = reinterpret_cast<float4 *>(workspace), *w1 = w0 + n, *w2 = w1 + n;
@@ -595,7 +597,7 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         k_primary<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, rays, n_pixels, spp, w0, w1);
     }
     LAUNCHED();
-    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st, record ? reinterpret_cast<__half *>(reinterpret_cast<float4 *>(record) + 6 * n) : nullptr,
+    rc = launch_field(P, n, nullptr, nullptr, w0, w1, w2, st, reinterpret_cast<__half *>(encoded),
                       /*pair=*/0);          // primary hits: the spp samples of a pixel share sectors, paired gathers do not pay
     if (rc) return rc;
     if (g_single_impl == 0) {
@@ -635,8 +637,8 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
     return IRIS_OK;
 }
 
-int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pixels, int32_t spp, const void *record, float *d_radiance,
-                         float *d_params, void *workspace, int64_t workspace_bytes, void *stream) {
+int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pixels, int32_t spp, const void *record, const void *encoded,
+                         float *d_radiance, float *d_params, void *workspace, int64_t workspace_bytes, void *stream) {
     if (!P) return fail(IRIS_ERR_INVALID, "params is NULL");
     if (n_pixels < 0 || spp <= 0) return fail(IRIS_ERR_INVALID, "bad arguments");
     if (n_pixels == 0) return IRIS_OK;
@@ -664,7 +666,8 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
     LAUNCHED();
     if (d_params) {
         const int64_t off = ((5 * 4 * n + 15) / 16) * 16;
-        __half *x_saved = reinterpret_cast<__half *>(const_cast<float4 *>(reinterpret_cast<const float4 *>(record)) + 6 * n);
+        if (reinterpret_cast<uintptr_t>(encoded) & 15) return fail(IRIS_ERR_INVALID, "encoded must be 16-byte aligned");
+        __half *x_saved = reinterpret_cast<__half *>(const_cast<void *>(encoded));
         return run_field_backward(P, n, nullptr, reinterpret_cast<const float4 *>(record) + 5 * n, d_mat, d_params,
                                   reinterpret_cast<unsigned char *>(workspace) + off, workspace_bytes - off, st, x_saved);
     }

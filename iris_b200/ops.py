@@ -100,7 +100,7 @@ class PathTracingSingle(torch.autograd.Function):
     def forward(ctx, radiance, params, scene, tables, rays, spp, sampler):
         need_rad = radiance is not None and radiance.requires_grad
         need_par = params is not None and params.requires_grad
-        L, rec = core.single_forward(scene, tables, rays, spp, sampler, want_record=need_rad or need_par)
+        L, rec = core.single_forward(scene, tables, rays, spp, sampler, want_record=need_rad or need_par, want_encoded=need_par)
         ctx.tables, ctx.spp, ctx.rec = tables, spp, rec
         ctx.need = (need_rad, need_par)
         ctx.shapes = (None if radiance is None else radiance.shape, None if params is None else params.shape)

@@ -515,10 +515,24 @@ def test_wavefront_bounce_equals_fused_bounce(small):
             L1, rec1 = _single(small, True)
             L2, _ = _single(small, False)
             assert torch.equal(rec0.view(torch.int32), rec1.view(torch.int32)), log2
+            assert torch.equal(rec0.encoded, rec1.encoded), log2
             assert torch.allclose(L0, L1, rtol=1e-5, atol=1e-7) and torch.allclose(L1, L2, rtol=1e-5, atol=1e-7), log2
     finally:
         core.C.check(lib.iris_set_option(b"single_impl", 1))
         core.C.check(lib.iris_set_option(b"single_chunk_log2", 23))
+    # the field adjoint from the kept encoded inputs equals the one that re-encodes from the record's hit points
+    dev = small["dev"]
+    U = torch.as_tensor(small["U"][:, :8]).to(dev)
+    rays = torch.as_tensor(small["rays"]).to(dev)
+    La, ra = core.single_forward(small["scene"], small["tables"], rays, small["spp"], core.Sampler(U=U), True)
+    Lb, rb = core.single_forward(small["scene"], small["tables"], rays, small["spp"], core.Sampler(U=U), True, want_encoded=False)
+    assert ra.encoded is not None and rb.encoded is None and torch.equal(ra.view(torch.int32), rb.view(torch.int32))
+    Gw = torch.as_tensor(small["Gw"]).to(dev)
+    n_par = 9216 + small["tables"].t["grid_f16"].numel()
+    da, db = torch.zeros(n_par, device=dev), torch.zeros(n_par, device=dev)
+    core.single_backward(small["tables"], Gw, small["spp"], ra, True, da)
+    core.single_backward(small["tables"], Gw, small["spp"], rb, True, db)
+    assert float(da.abs().sum()) > 0 and torch.allclose(da, db, rtol=1e-4, atol=1e-6 * float(da.abs().max()))
 
 
 def test_bake_queue_equals_fused_bake(small):
@@ -799,7 +813,7 @@ def test_c_abi_error_convention(small):
     rays = torch.as_tensor(small["rays"][:8]).to(dev)
     L = torch.zeros(8, 3, device=dev)
     ws = torch.zeros(64, dtype=torch.uint8, device=dev)
-    rc = lib.iris_single_forward(small["scene"].handle, ctypes.byref(P), C.ptr(rays), 8, 4, ctypes.byref(S), C.ptr(L), None, C.ptr(ws), ws.numel(), None)
+    rc = lib.iris_single_forward(small["scene"].handle, ctypes.byref(P), C.ptr(rays), 8, 4, ctypes.byref(S), C.ptr(L), None, None, C.ptr(ws), ws.numel(), None)
     assert rc == -4 and b"workspace" in lib.iris_last_error()
     assert lib.iris_brdf_shading_forward(C.ptr(L), C.ptr(L), C.ptr(L), C.ptr(L), 1, 8, C.ptr(L), None) == -1          # n_levels < 2
     assert lib.iris_slf_mark(C.ptr(o), None, 4, 0.0, 0.0, 32, C.ptr(out), None) == -1                                   # empty voxel range
