@@ -821,3 +821,76 @@ def test_c_abi_error_convention(small):
     assert lib.iris_launch_count() == l0
     with pytest.raises(RuntimeError, match="scene is NULL"):                                                               # the Python layer raises
         C.check(lib.iris_intersect(None, C.ptr(o), C.ptr(o), 4, C.ptr(out), None, None, None, None, None))
+
+
+@pytest.mark.gpu
+def test_full_size_properties_c3_scene():
+    """BASELINE configs[2] geometry (1M-triangle room, one 1280x960 view), where the oracle is too slow: size-independent properties.
+    (1) closest hits are self-consistent and identical between the static and the persistent kernel; (2) path_tracing_single is linear in
+    the radiance tables (x2 is exact in floating point, so only the order of the pixel atomics remains); (3) adjoint dot-product identity
+    <g, L(r1) - L(r0)> = <d_radiance, r1 - r0> for the emitter gradient; (4) same seed -> same image."""
+    dev = _gpu()
+    from iris_b200 import core, scenes
+    lib = core.C.lib()
+    sc = scenes.room(1_000_000, 16, seed=0)
+    scene = core.Scene(sc.vertices, sc.faces, 0)
+    assert scene.stats()["n_tris"] > 900_000
+    rays = torch.as_tensor(sc.camera_rays(1280, 960, view=1)).to(dev)
+    o, d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
+    t, prim, uv, p, n = scene.intersect_raw(o, d)
+    hit = prim >= 0
+    assert float(hit.float().mean()) > 0.99                                             # closed room
+    assert float((o + t[:, None] * d - p)[hit].abs().max()) < 1e-4                      # p on the ray at t
+    assert bool(((n * d).sum(-1)[hit] <= 0).all()) and float((n.norm(dim=-1)[hit] - 1).abs().max()) < 1e-5
+    assert bool((uv[hit] >= 0).all()) and bool((uv[hit].sum(-1) <= 1 + 1e-6).all()) and int(prim.max()) < sc.n_tris
+    F = torch.as_tensor(sc.faces).long().to(dev)
+    V = torch.as_tensor(sc.vertices).to(dev)
+    tri = V[F[prim[hit].long()]]
+    pb = tri[:, 0] * (1 - uv[hit].sum(-1, keepdim=True)) + tri[:, 1] * uv[hit][:, 0:1] + tri[:, 2] * uv[hit][:, 1:2]
+    assert float((pb - p[hit]).abs().max()) < 1e-4                                      # p inside the reported triangle at (u,v)
+    try:
+        core.C.check(lib.iris_set_option(b"intersect_impl", 1))
+        t2, prim2, uv2, p2, n2 = scene.intersect_raw(o, d)
+    finally:
+        core.C.check(lib.iris_set_option(b"intersect_impl", 0))
+    assert torch.equal(prim, prim2) and torch.equal(t, t2) and torch.equal(uv, uv2) and torch.equal(p, p2) and torch.equal(n, n2)
+
+    params = torch.empty(9216 + 27954112).uniform_(-1e-4, 1e-4, generator=torch.Generator().manual_seed(0))
+    em, slf = sc.emitter_dict(), sc.slf_dict(256)
+    tables = core.ShadingTables.from_dicts(dev, em, slf, params, sc.voxel_bounds())
+    spp = 4
+    smp = lambda: core.Sampler(seed=11)
+    r0 = tables.t["radiance"].clone()
+    L0, rec = core.single_forward(scene, tables, rays, spp, smp(), True, want_encoded=False)
+    L0b, _ = core.single_forward(scene, tables, rays, spp, smp(), False)
+    assert torch.isfinite(L0).all() and float(L0.mean()) > 0
+    assert torch.allclose(L0, L0b, rtol=1e-5, atol=1e-7)                                # (4)
+    # (2): both radiance tables x2
+    tables.set_radiance(r0 * 2)
+    tables.t["slf_radiance"] = tables.t["slf_radiance"] * 2
+    L2, _ = core.single_forward(scene, tables, rays, spp, smp(), False)
+    assert torch.allclose(L2, 2 * L0, rtol=1e-5, atol=1e-7)
+    tables.t["slf_radiance"] = tables.t["slf_radiance"] / 2
+    # (3): perturb only the emitter rows
+    g = torch.randn(L0.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    d_rad = core.single_backward(tables, g, spp, rec)
+    K = tables.K
+    r1 = r0.clone()
+    r1[:K] = r0[:K] * 1.5 + 0.25
+    tables.set_radiance(r1)
+    L1, _ = core.single_forward(scene, tables, rays, spp, smp(), False)
+    tables.set_radiance(r0)
+    lhs = float((g.double() * (L1.double() - L0.double())).sum())
+    rhs = float((d_rad.double() * (r1[:K].double() - r0[:K].double())).sum())
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1e-9), (lhs, rhs)
+    # (5) white furnace for the bake (configs[1] geometry): with every radiance table equal to 1 the diffuse map (sample weight 1,
+    #     brdf.py:86) is the fraction of rays that find an emitter or an occupied SLF voxel: never above 1, and 1 wherever the synthetic
+    #     SLF (sampled from the surfaces, a few voxels stay empty) covers what the pixel sees
+    tables.set_radiance(torch.ones_like(r0))
+    keep = tables.t["slf_radiance"]
+    tables.t["slf_radiance"] = torch.ones_like(keep)
+    pos, nrm = p[hit][::4].contiguous(), n[hit][::4].contiguous()
+    Ld = core.bake(scene, tables, 0, 1.0, pos, nrm, None, 16, core.Sampler(seed=5))
+    tables.t["slf_radiance"] = keep
+    tables.set_radiance(r0)
+    assert float(Ld.max()) <= 1 + 1e-5 and float(Ld.mean()) > 0.99 and float((Ld.min(dim=-1)[0] > 0.98).float().mean()) > 0.95, (float(Ld.min()), float(Ld.mean()))
