@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(TC5_ROWS) k_field_forward_tc5(IrisShadeParams 
                     const int64_t grow = tile * TC5_ROWS + r;
                     if (grow < n) *reinterpret_cast<uint4 *>(x_save + grow * 64 + c * 8) = *reinterpret_cast<const uint4 *>(sA + c * TC5_A_LBO + r * 16);
                 }
+                __syncwarp();      // the rows read above belong to other lanes of this warp, which overwrite them in their epilogue
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
