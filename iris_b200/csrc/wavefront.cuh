@@ -304,8 +304,9 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_b(IrisShadeParams P,
     const f3 pn = mk3(h0.x, h0.y, h0.z), nn = mk3(h1.x, h1.y, h1.z), wi = mk3(h2.x, h2.y, h2.z);
     const int32_t prim = __float_as_int(h2.w);
     float bpdf = h1.w;
-    const float4 m2 = has_field ? W.M2[i] : make_float4(0.f, 0.f, 0.f, 1.f);
-    const float m_next = has_field ? W.M1[i].w : 0.f;
+    const bool has_mat = has_field && prim >= 0;            // the field kernel only writes M1 / M2 for lanes whose ray hit something
+    const float4 m2 = has_mat ? W.M2[i] : make_float4(0.f, 0.f, 0.f, 1.f);
+    const float m_next = has_mat ? W.M1[i].w : 0.f;
     // model/emitter.py:180-221
     f3 Le = mk3(0.f, 0.f, 0.f);
     float epdf = 0.f;
