@@ -34,9 +34,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: tris, emitters, views per GPU, width, height, SPP, spp, estimator
     "c3": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32, brdf_grad=True,
-               desc="training step: path_tracing_single fwd+bwd with gradients to the BRDF field (hash grid + MLP) AND emitter radiance, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), random-init field, K=16, MIS on"),
+               desc="training step: path_tracing_single -> EmorCRF -> MSE, fwd+bwd with gradients to the BRDF field (hash grid + MLP), the emitter radiance and the CRF weight, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), random-init field, K=16, MIS on"),
     "c4": dict(tris=1_000_000, emitters=16, views=8, width=1280, height=960, SPP=256, spp=32, brdf_grad=False,
-               desc="train_emitter step: path_tracing_single fwd+bwd, emitter-radiance gradient, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), K=16, MIS on"),
+               desc="train_emitter step: path_tracing_single -> EmorCRF (fixed) -> MSE, fwd+bwd, emitter-radiance gradient, 1M-tri room, 8 views 1280x960/GPU, SPP=256 (8 x spp 32), K=16, MIS on"),
     "c5": dict(tris=5_000_000, emitters=16, views=64, width=1920, height=1440, SPP=128, spp=128, brdf_grad=True, strong=True,
                desc="scaling sweep: 5M-tri room, 64 views 1920x1440 in total (sharded over the GPUs), spp=128, path_tracing_single fwd+bwd, field + emitter gradients"),
     "c2": dict(tris=1_000_000, emitters=16, views=1, width=640, height=480, SPP=64, spp=64, brdf_grad=False, bake=True,
@@ -366,8 +366,15 @@ def main():
     want_par = bool(w.get("brdf_grad"))
     d_par_buf = torch.zeros(9216 + 27954112, device=dev) if want_par else None
 
+    from iris_b200.crf import EmorCRF
+    xs = np.linspace(0.0, 1.0, 1024, dtype=np.float32)     # synthetic response: gamma 2.2 mean curve + 11 smooth basis functions
+    crf = EmorCRF(dim=11, tables=(xs ** (1 / 2.2), np.stack([np.sin((k + 1) * np.pi * xs) * 0.05 for k in range(11)]).astype(np.float32))).to(dev)
+    crf.weight.requires_grad_(want_par)                      # train_emitter keeps the response fixed
+    exposure = torch.ones(1, device=dev)
+
     def step(host_inputs):
         """One training step of this rank: returns (loss tensor, d_radiance)."""
+        crf.weight.grad = None
         d_rad = torch.zeros(tables.K, 3, device=dev)
         if want_par:
             d_par_buf.zero_()
@@ -386,15 +393,20 @@ def main():
                                                      core.C.ptr(encs[c]), core.C.ptr(ws), ws.numel(), core.C.stream_ptr()))
                 L += Lc
             L /= n_chunks
-            diff = L - target[t0:t1]
-            loss += (diff * diff).sum() / (P * 3 * world)
-            dL = diff * (2.0 / (P * 3 * world * n_chunks))
+            # camera response + MSE, as every trainer does right after the estimator (train_emitter.py:191-193, train_brdf_crf.py:208-209):
+            # EmorCRF forward / adjoint kernels, gradient to L and -- in the train_brdf_crf configuration -- to the CRF weight
+            L.requires_grad_(True)
+            ldr = crf(L, exposure)
+            loss_t = ((ldr - target[t0:t1]) ** 2).sum() / (P * 3 * world)
+            loss_t.backward()
+            loss += loss_t.detach()
+            dL = L.grad / n_chunks
             for c in range(n_chunks):
                 P_ = tables.c()
                 core.C.check(lib.iris_single_backward(P_, core.C.ptr(dL), t1 - t0, spp, core.C.ptr(recs[c]), core.C.ptr(encs[c]), core.C.ptr(d_rad), core.C.ptr(d_par_buf),
                                                       core.C.ptr(ws) if want_par else None, ws.numel() if want_par else 0, core.C.stream_ptr()))
         if dist is not None:
-            idist.allreduce_gradients([d_rad, d_par_buf])
+            idist.allreduce_gradients([d_rad, d_par_buf, crf.weight.grad])
             dist.all_reduce(loss)
         if host_inputs:
             # the optimiser consumes gradients on the device; what leaves the GPU per step is the loss, the K x 3 emitter gradient
@@ -496,7 +508,8 @@ def main():
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="strong" if w.get("strong") else "weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cb,
                 scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
-                loss=float(loss), d_radiance_abs_sum=float(d_rad.abs().sum()), d_params_abs_sum=(float(d_par_l1) if d_par_l1 is not None else None))
+                loss=float(loss), d_radiance_abs_sum=float(d_rad.abs().sum()), d_params_abs_sum=(float(d_par_l1) if d_par_l1 is not None else None),
+                d_crf_weight_abs_sum=(float(crf.weight.grad.abs().sum()) if crf.weight.grad is not None else None))
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
