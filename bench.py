@@ -207,7 +207,7 @@ def bench_bake(a, w, sc, scene, tables, dev, config, stats):
     line = dict(metric="shading_map_bake_rays_per_sec", value=value, unit="rays/s", n_gpus=1, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms / a.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
                 gpu_launches=int(lib.iris_launch_count() - l0),
-                roofline=dict(bound="hbm", kernel="k_bake", achieved=value * bpr / 1e9, peak=peak, unit="GB/s", frac=value * bpr / 1e9 / peak, traffic=None,
+                roofline=dict(bound="hbm", kernel="k_bake_persistent", achieved=value * bpr / 1e9, peak=peak, unit="GB/s", frac=value * bpr / 1e9 / peak, traffic=None,
                               algorithmic_bytes_per_ray=bpr),
                 scene=dict(bvh_nodes=stats["n_nodes"], bvh_build_ms=stats["build_ms"], bvh_depth=stats["max_depth"]),
                 maps_finite=bool(all(torch.isfinite(o).all() for o in outs)))

@@ -154,6 +154,84 @@ __global__ void __launch_bounds__(IRIS_SORT_BLOCK) k_bake(SceneView S, IrisShade
     if (MODE == 1) pixel_accumulate(out1, pix, in_range, L1, inv);
 }
 
+// Persistent form of the bake: a fixed grid of warps pulls (pixel, sample) lanes from a global counter, generates the ray in
+// place, traverses, and a finished lane shades its hit, adds it to its pixel and pulls the next sample (same dynamic fetch as
+// k_trace_queue, without the queue: the generator and the radiance lookup are a few dozen instructions against ~300 warp
+// instructions of traversal per ray, so running them at partial occupancy costs little).
+template <int MODE>
+__global__ void __launch_bounds__(IRIS_BLOCK, 8) k_bake_persistent(SceneView S, IrisShadeParams P, IrisSampler smp, float roughness,
+                                                                   const float *__restrict__ position, const float *__restrict__ normal,
+                                                                   const float *__restrict__ wo_in, int64_t n_pixels, int spp, float *out0, float *out1,
+                                                                   unsigned long long *counter) {
+    uint2 stack[IRIS_STACK];
+    TravState T;
+    T.done = true;
+    int64_t ray = -1;
+    float w0 = 1.f, w1 = 0.f;
+    const int64_t n = n_pixels * spp;
+    const float inv = 1.f / (float)spp;
+    const unsigned lane = threadIdx.x & 31u;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, T.done);
+        if (T.done && ray >= 0) {
+            f3 hp, hn;
+            hit_surface(S, T.best, T.d, hp, hn);
+            int32_t e;
+            float epdf;
+            bool vn;
+            const f3 Le = radiance_at_hit(P, T.best, hp, e, epdf, vn);
+            const int64_t pix = ray / spp;
+            if (Le.x != 0.f || Le.y != 0.f || Le.z != 0.f) {
+                atomicAdd(out0 + 3 * pix, Le.x * w0 * inv);
+                atomicAdd(out0 + 3 * pix + 1, Le.y * w0 * inv);
+                atomicAdd(out0 + 3 * pix + 2, Le.z * w0 * inv);
+                if (MODE == 1) {
+                    atomicAdd(out1 + 3 * pix, Le.x * w1 * inv);
+                    atomicAdd(out1 + 3 * pix + 1, Le.y * w1 * inv);
+                    atomicAdd(out1 + 3 * pix + 2, Le.z * w1 * inv);
+                }
+            }
+            ray = -1;
+        }
+        if (need && !exhausted) {
+            const int cnt = __popc(need), leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (T.done) {
+                const int64_t r = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                if (r < n) {
+                    ray = r;
+                    const int64_t pix = r / spp;
+                    const f3 x = ld3(position, pix), nr = ld3(normal, pix);
+                    const float4 u = sample4(smp, r, 0);
+                    f3 wi;
+                    if (MODE == 0) {
+                        wi = diffuse_sampler(u.x, u.y, nr);
+                    } else {
+                        const f3 wo = ld3(wo_in, pix);
+                        wi = specular_sampler(u.x, u.y, roughness, wo, nr);
+                        specular_weights(wi, wo, nr, roughness, w0, w1);
+                    }
+                    trav_init(T, mk3(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z), wi,
+                              __int_as_float(0x7f800000), -1, 0);
+                }
+            }
+            if ((int64_t)base + cnt >= n) exhausted = true;
+        }
+        unsigned active = __ballot_sync(0xffffffffu, !T.done);
+        if (active == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        do {
+            if (!T.done) trav_step(S, T, stack);
+            active = __ballot_sync(0xffffffffu, !T.done);
+        } while (active != 0u && (exhausted || __popc(active) >= IRIS_PERSIST_THRESH));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ path_tracing_single
 // Workspace per lane: three float4.
 //   w0 = (x0.xyz, code)   code: -2 = continue (valid_next), -1 = miss, >= 0 = emitter row hit by the primary ray

@@ -536,8 +536,9 @@ def test_wavefront_bounce_equals_fused_bounce(small):
 
 
 def test_bake_queue_equals_fused_bake(small):
-    """bake runs as one fused kernel with a block-level direction sort by default; the ray-queue form (generate -> persistent
-    trace -> shade) is kept behind a switch.  Same rays, same arithmetic: equal up to the order of the per-pixel float atomics."""
+    """bake runs as one persistent kernel (dynamic sample fetch, generator and radiance lookup in the kernel) by default; the fused
+    kernel with a block-level direction sort and the ray-queue form (generate -> persistent trace -> shade) are kept behind a
+    switch.  Same rays, same arithmetic: equal up to the order of the per-pixel float atomics."""
     from iris_b200 import core
     lib = core.C.lib()
     dev, spp = small["dev"], small["spp"]
@@ -547,7 +548,7 @@ def test_bake_queue_equals_fused_bake(small):
     smp = core.Sampler(seed=5)
     try:
         outs = []
-        for impl, log2 in ((0, 23), (1, 23), (1, 10)):
+        for impl, log2 in ((0, 23), (1, 23), (1, 10), (2, 23)):      # 2: persistent warps, generator + lookup in the kernel
             core.C.check(lib.iris_set_option(b"bake_impl", impl))
             core.C.check(lib.iris_set_option(b"single_chunk_log2", log2))
             d = core.bake(small["scene"], small["tables"], 0, 1.0, pos, nrm, None, spp, smp)
