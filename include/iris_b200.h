@@ -250,7 +250,16 @@ int iris_crf_backward(const float *hdr, const float *exposure, int32_t exposure_
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t iris_launch_count(void);
 
-/* Implementation switches used for A/B measurements: "field_forward_impl" = 0 (mma.sync warp tiles) | 1 (tcgen05 + TMEM 128-row tiles). */
+/* Implementation switches (process-wide; every alternative is tested equal to the default).  Defaults first:
+ *   "field_forward_impl"      1 tcgen05 + TMEM 128-row tiles | 0 mma.sync warp tiles
+ *   "single_impl"             1 wavefront bounce (generate -> persistent ray-queue trace -> shade) | 0 one fused kernel
+ *   "single_chunk_log2"       23: samples per ray-queue chunk = 2^value (10..30)
+ *   "wave_impl"               1 path_tracing / det / indirect bounces through the ray queue | 0 fused bounce kernel
+ *   "bake_impl"               2 persistent kernel, generator and radiance lookup inside | 0 fused kernel with block-level direction sort | 1 ray queue
+ *   "intersect_impl"          0 one ray per lane (best on camera rays) | 1 persistent warps with dynamic ray fetch (best on incoherent rays)
+ *   "persist_ctas_per_sm"     8: resident CTAs per SM of the persistent kernels (1..16)
+ *   "tc5_ctas_per_sm" 4, "field_smem_carveout_pct" 70, "trace_smem_carveout_pct" -1: occupancy / L1 tuning of the field and tracing kernels
+ * Unknown names or out-of-range values return IRIS_ERR_INVALID. */
 int iris_set_option(const char *name, int value);
 
 /* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its own stream.
