@@ -788,6 +788,48 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 
 // dW[o][i] += sum_s s_s * D[s][o] * H[s][i] for one 32-sample tile: warp w owns rows [16w,16w+16) (MT16 = number of 16-row
 // slices that exist: 4 for the 64-row matrices, 1 for W3)
+// acc (16 x 64 slice of dW, rows mrow0..mrow0+15) += sum over the tile's 32 samples of s * D[sample][row] * H[sample][col], on
+// mma.sync m16n8k8 TF32.  The MMA's row / column labels are free as long as the A/B fragments and the accumulator agree, so they are
+// chosen for wide shared-memory loads: MMA row g <-> feature mrow0 + 2g, row g+8 <-> mrow0 + 2g + 1 (one 4-byte load gives both),
+// MMA column g of n-tile nt <-> feature 8g + nt (one 16-byte load gives the lane its column of all eight n-tiles).  Against scalar
+// 2-byte loads this is 16 instead of 80 shared-memory loads per lane and call; wgrad_store() undoes the permutation.
+#ifndef FIELD_WGRAD_SCALAR_LOADS
+__device__ __forceinline__ void wgrad_tile(const __half *D, int ldd, const __half *H, const float *sc, int mrow0, float acc[8][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int k0 = 8 * ks;
+        const float s0 = sc[k0 + t], s1 = sc[k0 + t + 4];
+        const float2 d0 = __half22float2(*reinterpret_cast<const __half2 *>(D + (k0 + t) * ldd + mrow0 + 2 * g));
+        const float2 d1 = __half22float2(*reinterpret_cast<const __half2 *>(D + (k0 + t + 4) * ldd + mrow0 + 2 * g));
+        uint32_t a[4];
+        a[0] = to_tf32(d0.x * s0);
+        a[1] = to_tf32(d0.y * s0);
+        a[2] = to_tf32(d1.x * s1);
+        a[3] = to_tf32(d1.y * s1);
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(H + (k0 + t) * FIELD_LD + 8 * g);
+        const uint4 h1 = *reinterpret_cast<const uint4 *>(H + (k0 + t + 4) * FIELD_LD + 8 * g);
+        const uint32_t w0[4] = {h0.x, h0.y, h0.z, h0.w}, w1[4] = {h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float2 p0 = __half22float2(*reinterpret_cast<const __half2 *>(&w0[nt >> 1]));
+            const float2 p1 = __half22float2(*reinterpret_cast<const __half2 *>(&w1[nt >> 1]));
+            uint32_t b[2];
+            b[0] = __float_as_uint((nt & 1) ? p0.y : p0.x);
+            b[1] = __float_as_uint((nt & 1) ? p1.y : p1.x);
+            mma1688_tf32(acc[nt], a, b);
+        }
+    }
+}
+// adds a warp's accumulators to dW (row-major [out][64]): accumulator (nt, k) holds MMA row g (+8 for k >= 2), MMA column 2t + (k & 1)
+__device__ __forceinline__ void wgrad_store(float *dW, int mrow0, const float acc[8][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(dW + (mrow0 + 2 * g + (k >> 1)) * 64 + 8 * (2 * t + (k & 1)) + nt, acc[nt][k]);
+}
+#else
 __device__ __forceinline__ void wgrad_tile(const __half *D, int ldd, const __half *H, const float *sc, int mrow0, float acc[8][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -808,6 +850,15 @@ __device__ __forceinline__ void wgrad_tile(const __half *D, int ldd, const __hal
         }
     }
 }
+
+__device__ __forceinline__ void wgrad_store(float *dW, int mrow0, const float acc[8][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(dW + (mrow0 + g + 8 * (k >> 1)) * 64 + 8 * nt + 2 * t + (k & 1), acc[nt][k]);
+}
+#endif
 
 // Shared-memory image of one 32-sample tile: X | h1 | h2 | dh2^ | dh1^ (32 x 64 fp16, ld 72) | dy^ (32 x 16, ld 24) | s (32 floats)
 #define FIELD_WGRAD_TILE_BYTES (5 * 32 * FIELD_LD * 2 + 32 * FIELD_LD3 * 2 + 32 * 4)
@@ -886,16 +937,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_field_backward_wgrad(FieldAct ac
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // one atomic per weight per CTA
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const int r = 16 * warp + g, c = 8 * nt + 2 * t;
-        atomicAdd(d_mlp + r * 64 + c, a1[nt][0]); atomicAdd(d_mlp + r * 64 + c + 1, a1[nt][1]);
-        atomicAdd(d_mlp + (r + 8) * 64 + c, a1[nt][2]); atomicAdd(d_mlp + (r + 8) * 64 + c + 1, a1[nt][3]);
-        atomicAdd(d_mlp + 4096 + r * 64 + c, a2[nt][0]); atomicAdd(d_mlp + 4096 + r * 64 + c + 1, a2[nt][1]);
-        atomicAdd(d_mlp + 4096 + (r + 8) * 64 + c, a2[nt][2]); atomicAdd(d_mlp + 4096 + (r + 8) * 64 + c + 1, a2[nt][3]);
-        if (warp == 0) {
-            atomicAdd(d_mlp + 8192 + g * 64 + c, a3[nt][0]); atomicAdd(d_mlp + 8192 + g * 64 + c + 1, a3[nt][1]);
-            atomicAdd(d_mlp + 8192 + (g + 8) * 64 + c, a3[nt][2]); atomicAdd(d_mlp + 8192 + (g + 8) * 64 + c + 1, a3[nt][3]);
-        }
-    }
+    wgrad_store(d_mlp, 16 * warp, a1);
+    wgrad_store(d_mlp + 4096, 16 * warp, a2);
+    if (warp == 0) wgrad_store(d_mlp + 8192, 0, a3);
 }
