@@ -148,10 +148,10 @@ int iris_field_backward(const IrisShadeParams *params, const float *position, co
  *   record: NULL for inference; otherwise >= iris_single_record_bytes(B,spp) bytes that the adjoint
  *   replays (per sample 96 bytes: emitter rows + coefficients of the three radiance gathers, the 3x3
  *   sparse Jacobian of the sample's radiance wrt albedo/roughness/metallic, the hit point).
- *   encoded: optional (NULL, or >= iris_single_encoded_bytes(B,spp) = 128 bytes per sample, 16-byte aligned): the forward keeps
- *   every sample's 64 fp16 hash-grid features there; a backward with d_params != NULL that is given the same array reads them
- *   instead of gathering the grid a second time (without it the adjoint re-encodes from the hit points in the record).  Pass
- *   NULL when only the emitter gradient is wanted (train_emitter.py).
+ *   encoded: NULL, or >= iris_single_encoded_bytes(B,spp) = 128 bytes per sample, 16-byte aligned.  Given: the forward keeps every
+ *   sample's 64 fp16 hash-grid features there and writes the Jacobian words of the record, and iris_single_backward (which must be
+ *   handed the same array) can produce d_mat / d_params without gathering the grid again.  NULL: the record is the emitter-gradient-only
+ *   form of train_emitter.py -- no Jacobians computed or stored, iris_single_backward with d_params != NULL returns IRIS_ERR_INVALID.
  *   workspace: >= iris_single_workspace_bytes(B,spp): three 16-byte words per sample and the ray queue
  *   of one chunk (the secondary bounce runs as generate -> persistent ray-queue trace -> shade).
  * iris_single_backward: dL (B,3) -> d_radiance (K,3) accumulated; d_mat (B*spp,5) written (feed it,

@@ -621,7 +621,9 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         LAUNCHED();
         return IRIS_OK;
     }
-    // wavefront bounce: generate rays -> persistent trace -> shade, in chunks whose queue stays small
+    // wavefront bounce: generate rays -> persistent trace -> shade, in chunks whose queue stays small.  Record mode: 0 inference,
+    // 1 emitter gradient only (no `encoded` array given: the BRDF Jacobians are neither computed nor stored), 2 full
+    const int rec_mode = record ? (encoded ? 2 : 1) : 0;
     const int64_t nc_max = single_chunk_samples(n);
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(w2 + n);
     float4 *ro = reinterpret_cast<float4 *>(counters + SINGLE_MAX_CHUNKS), *rd = ro + 2 * nc_max, *hit = rd + 2 * nc_max, *state = hit + 2 * nc_max;
@@ -631,8 +633,9 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         const int64_t nc = std::min(nc_max, n - i0);
         {
             ProfScope ps(K_SINGLE_GEN, st);
-            if (record) k_single_gen<true><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
-            else k_single_gen<false><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
+            if (rec_mode == 2) k_single_gen<2><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
+            else if (rec_mode == 1) k_single_gen<1><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
+            else k_single_gen<0><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(*P, *sampler, rays, i0, nc, spp, w0, w1, w2, ro, rd, state);
         }
         LAUNCHED();
         {
@@ -643,8 +646,10 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         LAUNCHED();
         {
             ProfScope ps(K_SINGLE_SHADE, st);
-            if (record) k_single_shade<true><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, reinterpret_cast<float4 *>(record));
-            else k_single_shade<false><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, nullptr);
+            float4 *rec4 = reinterpret_cast<float4 *>(record);
+            if (rec_mode == 2) k_single_shade<2><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, rec4);
+            else if (rec_mode == 1) k_single_shade<1><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, rec4);
+            else k_single_shade<0><<<blocks_for(nc), IRIS_BLOCK, 0, st>>>(view_of(s), *P, i0, nc, n, spp, w0, rd, hit, state, L, nullptr);
         }
         LAUNCHED();
     }
@@ -663,10 +668,11 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
     const int64_t n = n_pixels * spp;
     float *d_mat = nullptr;
     if (d_params) {
+        if (!encoded) return fail(IRIS_ERR_INVALID, "the field gradient needs the `encoded` array the forward was given (a record made without it holds no BRDF Jacobians)");
         if (!P->grid_f16 || !P->mlp_f16) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
         if (!workspace || workspace_bytes < iris_single_workspace_bytes(n_pixels, spp)) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
     }
-    if (workspace) {   // d_mat (n,5) = J^T g is left at the start of the workspace (also without d_params, for inspection)
+    if (workspace && encoded) {   // d_mat (n,5) = J^T g is left at the start of the workspace (also without d_params, for inspection)
         if (workspace_bytes < 5 * 4 * n) return fail(IRIS_ERR_WORKSPACE, "workspace too small for d_mat");
         if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(IRIS_ERR_INVALID, "workspace must be 16-byte aligned");
         d_mat = reinterpret_cast<float *>(workspace);

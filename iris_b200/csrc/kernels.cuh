@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_bake_shade(SceneView S, IrisShad
 //   s0 = (L_nee.rgb if unoccluded, pdf_b)   s1 = (wb.rgb, e_nee)                      e_nee < 0: no shadow ray
 //   RECORD: s2 = (c_nee.rgb, JaN.x) s3 = (JaN.yz, JrN.xy) s4 = (JrN.z, JmN.xyz) s5 = (Jb.da, Jb.dr.x) s6 = (Jb.dr.yz, Jb.dm.xy) s7 = (Jb.dm.z,..)
 #define IRIS_SINGLE_STATE_STREAMS 8
-template <bool RECORD>
+// REC: 0 = inference, 1 = record for the emitter gradient only (no BRDF Jacobians: train_emitter.py), 2 = full record
+template <int REC>
 __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays, int64_t i0, int64_t nc, int spp,
                                                             const float4 *__restrict__ w0, const float4 *__restrict__ w1, const float4 *__restrict__ w2,
                                                             float4 *__restrict__ ro, float4 *__restrict__ rd, float4 *__restrict__ st) {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
                 f3 f;
                 float pdf_b;
                 BrdfJac J;
-                eval_brdf<RECORD>(wi, wo, n0, mat, f, pdf_b, &J);
+                eval_brdf<REC == 2>(wi, wo, n0, mat, f, pdf_b, &J);
                 pdf_b *= G;
                 float w = (pdf_e > 0.f && !isinf(pdf_b)) ? pdf_e * pdf_e / fmaxf(pdf_e * pdf_e + pdf_b * pdf_b, 1e-6f) : 0.f;
                 if (isinf(pdf_e) || pdf_b == 0.f) w = 1.f;
@@ -440,22 +441,20 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
                 const f3 W = emitter_radiance(P, e) * s;
                 L_nee = f * W;
                 e_nee = e;
-                if (RECORD) {
-                    c_nee = f * s;
-                    JaN = J.da * W; JrN = J.dr * W; JmN = J.dm * W;
-                }
+                if (REC >= 1) c_nee = f * s;
+                if (REC == 2) { JaN = J.da * W; JrN = J.dr * W; JmN = J.dm * W; }
             }
         }
         f3 wi, wb;
         float pdf_b;
         BrdfJac J;
-        sample_brdf<RECORD>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
+        sample_brdf<REC == 2>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
         ro_b = make_float4(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
         rd_b = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
         st[j] = make_float4(L_nee.x, L_nee.y, L_nee.z, pdf_b);
         st[nc + j] = make_float4(wb.x, wb.y, wb.z, __int_as_float(e_nee));
-        if (RECORD) {
-            st[2 * nc + j] = make_float4(c_nee.x, c_nee.y, c_nee.z, JaN.x);
+        if (REC >= 1) st[2 * nc + j] = make_float4(c_nee.x, c_nee.y, c_nee.z, JaN.x);
+        if (REC == 2) {
             st[3 * nc + j] = make_float4(JaN.y, JaN.z, JrN.x, JrN.y);
             st[4 * nc + j] = make_float4(JrN.z, JmN.x, JmN.y, JmN.z);
             st[5 * nc + j] = make_float4(J.da.x, J.da.y, J.da.z, J.dr.x);
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
 }
 
 // path_tracing_single, shading half: visibility, emitter / SLF radiance at the BSDF hit, MIS, the adjoint record, pixel mean.
-template <bool RECORD>
+template <int REC>
 __global__ void __launch_bounds__(IRIS_BLOCK) k_single_shade(SceneView S, IrisShadeParams P, int64_t i0, int64_t nc, int64_t n, int spp,
                                                               const float4 *__restrict__ w0, const float4 *__restrict__ rd, const float4 *__restrict__ hit,
                                                               const float4 *__restrict__ st, float *L_out, float4 *__restrict__ rec) {
@@ -491,11 +490,14 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_shade(SceneView S, IrisSh
             const float4 s0 = st[j], s1 = st[nc + j];
             if (__float_as_int(s1.w) >= 0 && __float_as_int(hit[j].w) < 0) {
                 L = mk3(s0.x, s0.y, s0.z);
-                if (RECORD) {
-                    const float4 s2 = st[2 * nc + j], s3 = st[3 * nc + j], s4 = st[4 * nc + j];
+                if (REC >= 1) {
+                    const float4 s2 = st[2 * nc + j];
                     e_nee = __float_as_int(s1.w);
                     c_nee = mk3(s2.x, s2.y, s2.z);
-                    Ja = mk3(s2.w, s3.x, s3.y); Jr = mk3(s3.z, s3.w, s4.x); Jm = mk3(s4.y, s4.z, s4.w);
+                    if (REC == 2) {
+                        const float4 s3 = st[3 * nc + j], s4 = st[4 * nc + j];
+                        Ja = mk3(s2.w, s3.x, s3.y); Jr = mk3(s3.z, s3.w, s4.x); Jm = mk3(s4.y, s4.z, s4.w);
+                    }
                 }
             }
             const float4 dq = rd[nc + j];
@@ -516,19 +518,21 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_shade(SceneView S, IrisSh
             float w = (pdf_b > 0.f && !isinf(pdf_e)) ? pdf_b * pdf_b / (pdf_e * pdf_e + pdf_b * pdf_b) : 0.f;
             if (isinf(pdf_b) || pdf_e == 0.f) w = 1.f;
             L = L + wb * Le * w;
-            if (RECORD) {
+            if (REC >= 1 && eh >= 0) { e_b = eh; c_b = wb * w; }
+            if (REC == 2) {
                 const float4 s5 = st[5 * nc + j], s6 = st[6 * nc + j], s7 = st[7 * nc + j];
-                if (eh >= 0) { e_b = eh; c_b = wb * w; }
                 const f3 Lw = Le * w;
                 Ja = Ja + mk3(s5.x, s5.y, s5.z) * Lw; Jr = Jr + mk3(s5.w, s6.x, s6.y) * Lw; Jm = Jm + mk3(s6.z, s6.w, s7.x) * Lw;
             }
         }
-        if (RECORD) {
+        if (REC >= 1) {
             rec[i] = make_float4(__int_as_float(e0), __int_as_float(e_nee), __int_as_float(e_b), 0.f);
             rec[n + i] = make_float4(c_nee.x, c_nee.y, c_nee.z, c_b.x);
             rec[2 * n + i] = make_float4(c_b.y, c_b.z, Ja.x, Ja.y);
-            rec[3 * n + i] = make_float4(Ja.z, Jr.x, Jr.y, Jr.z);
-            rec[4 * n + i] = make_float4(Jm.x, Jm.y, Jm.z, 0.f);
+            if (REC == 2) {        // the Jacobian words are only written (and only read back) when the field gradient is wanted
+                rec[3 * n + i] = make_float4(Ja.z, Jr.x, Jr.y, Jr.z);
+                rec[4 * n + i] = make_float4(Jm.x, Jm.y, Jm.z, 0.f);
+            }
             rec[5 * n + i] = a;
         }
     }

@@ -520,19 +520,26 @@ def test_wavefront_bounce_equals_fused_bounce(small):
     finally:
         core.C.check(lib.iris_set_option(b"single_impl", 1))
         core.C.check(lib.iris_set_option(b"single_chunk_log2", 23))
-    # the field adjoint from the kept encoded inputs equals the one that re-encodes from the record's hit points
+    # a record made WITHOUT the encoded array is the emitter-gradient-only form (train_emitter.py): same image, same emitter words and
+    # emitter gradient, no BRDF Jacobians -- asking it for the field gradient is an error, not a silent zero
     dev = small["dev"]
     U = torch.as_tensor(small["U"][:, :8]).to(dev)
     rays = torch.as_tensor(small["rays"]).to(dev)
     La, ra = core.single_forward(small["scene"], small["tables"], rays, small["spp"], core.Sampler(U=U), True)
     Lb, rb = core.single_forward(small["scene"], small["tables"], rays, small["spp"], core.Sampler(U=U), True, want_encoded=False)
-    assert ra.encoded is not None and rb.encoded is None and torch.equal(ra.view(torch.int32), rb.view(torch.int32))
+    assert ra.encoded is not None and rb.encoded is None and torch.allclose(La, Lb, rtol=1e-5, atol=1e-7)
+    n = rays.shape[0] * small["spp"]
+    wa, wb = ra.view(torch.int32).view(6, n, 4), rb.view(torch.int32).view(6, n, 4)
+    assert torch.equal(wa[0], wb[0]) and torch.equal(wa[1], wb[1]) and torch.equal(wa[2][:, :2], wb[2][:, :2]) and torch.equal(wa[5], wb[5])
     Gw = torch.as_tensor(small["Gw"]).to(dev)
+    assert torch.equal(core.single_backward(small["tables"], Gw, small["spp"], ra), core.single_backward(small["tables"], Gw, small["spp"], rb)) or \
+        torch.allclose(core.single_backward(small["tables"], Gw, small["spp"], ra), core.single_backward(small["tables"], Gw, small["spp"], rb), rtol=1e-5)
     n_par = 9216 + small["tables"].t["grid_f16"].numel()
-    da, db = torch.zeros(n_par, device=dev), torch.zeros(n_par, device=dev)
+    with pytest.raises(RuntimeError, match="encoded"):
+        core.single_backward(small["tables"], Gw, small["spp"], rb, True, torch.zeros(n_par, device=dev))
+    da = torch.zeros(n_par, device=dev)
     core.single_backward(small["tables"], Gw, small["spp"], ra, True, da)
-    core.single_backward(small["tables"], Gw, small["spp"], rb, True, db)
-    assert float(da.abs().sum()) > 0 and torch.allclose(da, db, rtol=1e-4, atol=1e-6 * float(da.abs().max()))
+    assert float(da.abs().sum()) > 0
 
 
 def test_bake_queue_equals_fused_bake(small):
