@@ -341,6 +341,16 @@ int iris_scene_stats(const IrisScene *s, IrisSceneStats *out) {
     return IRIS_OK;
 }
 
+// next slot of the counter ring, zeroed on the caller's stream
+static std::atomic<unsigned> g_counter_slot{0};
+static int next_ray_counter(unsigned long long **out, cudaStream_t st) {
+    void *base = nullptr;
+    CUDA_TRY(cudaGetSymbolAddress(&base, g_ray_counters));
+    *out = reinterpret_cast<unsigned long long *>(base) + (g_counter_slot.fetch_add(1) % IRIS_COUNTER_RING);
+    CUDA_TRY(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
+    return IRIS_OK;
+}
+
 int iris_intersect(const IrisScene *s, const float *o, const float *d, int64_t n, float *t, int32_t *prim, float *uv, float *p, float *nrm,
                    void *stream) {
     if (!s) return fail(IRIS_ERR_INVALID, "scene is NULL");
@@ -350,12 +360,12 @@ int iris_intersect(const IrisScene *s, const float *o, const float *d, int64_t n
     {
         ProfScope ps(K_INTERSECT, (cudaStream_t)stream);
         if (g_intersect_impl == 1) {
-            void *cnt = nullptr;
-            CUDA_TRY(cudaGetSymbolAddress(&cnt, g_ray_counter));
-            CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+            unsigned long long *cnt = nullptr;
+            int rc = next_ray_counter(&cnt, (cudaStream_t)stream);
+            if (rc) return rc;
             const int64_t want = (n + IRIS_BLOCK - 1) / IRIS_BLOCK;
             const int grid = (int)std::min<int64_t>(want, (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
-            k_intersect_persistent<<<grid, IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
+            k_intersect_persistent<<<grid, IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm, cnt);
         } else {
             k_intersect<<<blocks_for(n), IRIS_BLOCK, 0, (cudaStream_t)stream>>>(view_of(s), o, d, n, t, prim, uv, p, nrm);
         }
@@ -419,15 +429,12 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
     if (mode == 1) CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     const int64_t n = n_pixels * spp;
     if (g_bake_impl == 2) {           // persistent warps, generator and radiance lookup in the kernel
-        void *cnt = nullptr;
-        CUDA_TRY(cudaGetSymbolAddress(&cnt, g_ray_counter));
-        CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+        unsigned long long *cnt = nullptr;
+        if ((rc = next_ray_counter(&cnt, st))) return rc;
         ProfScope ps(mode == 0 ? K_BAKE_DIFFUSE : K_BAKE_SPECULAR, st);
         const int grid = (int)std::min<int64_t>(blocks_for(n), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
-        if (mode == 0) k_bake_persistent<0><<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1,
-                                                                       reinterpret_cast<unsigned long long *>(cnt));
-        else k_bake_persistent<1><<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1,
-                                                               reinterpret_cast<unsigned long long *>(cnt));
+        if (mode == 0) k_bake_persistent<0><<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1, cnt);
+        else k_bake_persistent<1><<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), *P, *sampler, roughness, position, normal, wo, n_pixels, spp, out0, out1, cnt);
         LAUNCHED();
         return IRIS_OK;
     }

@@ -30,10 +30,13 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_intersect(SceneView S, const flo
 #ifndef IRIS_PERSIST_THRESH
 #define IRIS_PERSIST_THRESH 20
 #endif
-__device__ unsigned long long g_ray_counter;
+// fetch counters of the persistent kernels that have no caller workspace (ray_intersect, bake): a ring, one slot per launch, so that
+// launches in flight on different streams never share a counter
+#define IRIS_COUNTER_RING 1024
+__device__ unsigned long long g_ray_counters[IRIS_COUNTER_RING];
 
 __global__ void __launch_bounds__(IRIS_BLOCK) k_intersect_persistent(SceneView S, const float *__restrict__ o, const float *__restrict__ d, int64_t n,
-                                                                      float *t, int32_t *prim, float *uv, float *p, float *nrm) {
+                                                                      float *t, int32_t *prim, float *uv, float *p, float *nrm, unsigned long long *counter) {
     uint2 stack[IRIS_STACK];
     TravState T;
     T.done = true;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_intersect_persistent(SceneView S
         if (need && !exhausted) {
             const int cnt = __popc(need), leader = __ffs(need) - 1;
             unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(&g_ray_counter, (unsigned long long)cnt);
+            if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
             base = __shfl_sync(0xffffffffu, base, leader);
             if (T.done) {
                 const int64_t r = (int64_t)base + __popc(need & ((1u << lane) - 1u));
