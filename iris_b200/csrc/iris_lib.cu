@@ -482,7 +482,10 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
 
 static int launch_field(const IrisShadeParams *P, int64_t n, const float *position, float *mat, const float4 *w0, float4 *w1, float4 *w2, cudaStream_t st,
                         __half *x_save = nullptr, int pair = 1) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};       // function attributes belong to the device context: set them once per device
+    int cur_dev = 0;
+    CUDA_TRY(cudaGetDevice(&cur_dev));
+    bool &attr_done = attr_done_dev[cur_dev & 63];
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_field_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM_BYTES));
@@ -531,7 +534,10 @@ int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t 
 #define FIELD_BWD_CHUNK (1ll << FIELD_BWD_CHUNK_LOG2)
 static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *position, const float4 *r5, const float *d_mat, float *d_params,
                               void *workspace, int64_t workspace_bytes, cudaStream_t st, __half *x_saved = nullptr) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};       // function attributes belong to the device context: set them once per device
+    int cur_dev = 0;
+    CUDA_TRY(cudaGetDevice(&cur_dev));
+    bool &attr_done = attr_done_dev[cur_dev & 63];
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_field_backward_dgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_BWD_SMEM_BYTES));
