@@ -15,10 +15,12 @@ from oracle.intersect import OracleScene
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def host_lib(tmp_path_factory):
+@pytest.fixture(scope="module", params=[0, 1], ids=["nodes80B", "nodes128B_fp16"])
+def host_lib(tmp_path_factory, request):
+    # both node formats of bvh8.h: the compact default and the compile-time 128-byte fp16 variant kept for A/B measurements
     out = str(tmp_path_factory.mktemp("host") / "libtraverse_host.so")
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-I/usr/local/cuda/include", "-o", out,
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-DIRIS_NODE_FP16=%d" % request.param,
+                           "-I/usr/local/cuda/include", "-o", out,
                            os.path.join(ROOT, "tests", "host", "traverse_host.cpp"), os.path.join(ROOT, "iris_b200", "csrc", "bvh_build.cpp")])
     L = ctypes.CDLL(out)
     L.host_trace.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6
