@@ -529,7 +529,7 @@ int iris_field_forward(const IrisShadeParams *P, const float *position, int64_t 
 }
 
 #ifndef FIELD_BWD_CHUNK_LOG2
-#define FIELD_BWD_CHUNK_LOG2 22
+#define FIELD_BWD_CHUNK_LOG2 23
 #endif
 #define FIELD_BWD_CHUNK (1ll << FIELD_BWD_CHUNK_LOG2)
 static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *position, const float4 *r5, const float *d_mat, float *d_params,
