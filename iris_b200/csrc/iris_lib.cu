@@ -11,6 +11,7 @@
 #include "bvh_device.cuh"
 #include "field.cuh"
 #include "field_tc5.cuh"
+#include "field_bwd_tc5.cuh"
 #include "kernels.cuh"
 #include "wavefront.cuh"
 #include "crf.cuh"
@@ -78,6 +79,7 @@ static int g_sm_count = 0;
 static int g_tc5_ctas = 4;      // tcgen05 kernel: CTAs per SM (34.9 KB smem, 64 TMEM columns each)
 static int g_single_impl = 1;      // 1: wavefront bounce (k_single_gen -> k_trace_queue -> k_single_shade), 0: fused k_bounce_single
 static int64_t g_single_chunk = 8 << 20;   // samples per wavefront chunk
+static int g_field_bwd_impl = 1;   // 1: fused tcgen05 dgrad + wgrad kernel (field_bwd_tc5.cuh; used whenever the encoded inputs are available); 0: dgrad (mma.sync) + wgrad (TF32 split-K) kernels
 static int g_bake_impl = 2;        // 2: persistent warps with the generator / radiance lookup in the kernel (k_bake_persistent, default: +20-44 % over 0
                                    //    except on mirror-like lobes), 0: fused k_bake with block-level direction sort, 1: through the ray queue
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
@@ -213,6 +215,7 @@ int iris_set_option(const char *name, int value) {
         CUDA_TRY(cudaFuncSetAttribute(k_bake<1>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
         return IRIS_OK;
     }
+    if (name && std::strcmp(name, "field_backward_impl") == 0 && (value == 0 || value == 1)) { g_field_bwd_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "wave_impl") == 0 && (value == 0 || value == 1)) { g_wave_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "bake_impl") == 0 && value >= 0 && value <= 2) { g_bake_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
@@ -552,7 +555,19 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
         if (x_saved) act.X = x_saved + 64 * c0;        // encoded inputs kept by the forward pass: not recomputed, not copied
         const int64_t tiles = (m + FIELD_BWD_BLOCK - 1) / FIELD_BWD_BLOCK;
         const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * (512 / FIELD_BWD_BLOCK));
-        {
+        const bool fused = g_field_bwd_impl == 1 && x_saved != nullptr;          // EXPERIMENTAL one-kernel dgrad + wgrad on tcgen05 (field_bwd_tc5.cuh)
+        if (fused) {
+            static bool fattr[64] = {false};
+            if (!fattr[cur_dev & 63]) {
+                CUDA_TRY(cudaFuncSetAttribute(k_field_backward_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT5_SMEM_BYTES));
+                CUDA_TRY(cudaFuncSetAttribute(k_field_backward_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT5_SMEM_BYTES));
+                fattr[cur_dev & 63] = true;
+            }
+            ProfScope ps(K_FIELD_BACKWARD, st);
+            const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * 2);
+            if (r5) k_field_backward_tc5<true><<<gf, TC5_ROWS, BT5_SMEM_BYTES, st>>>(*P, m, r5 + c0, d_mat + 5 * c0, act.X, act.dx, act.s, d_params);
+            else k_field_backward_tc5<false><<<gf, TC5_ROWS, BT5_SMEM_BYTES, st>>>(*P, m, nullptr, d_mat + 5 * c0, act.X, act.dx, act.s, d_params);
+        } else {
             ProfScope ps(K_FIELD_BACKWARD, st);
             if (r5) k_field_backward_dgrad<true><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, nullptr, r5 + c0, d_mat + 5 * c0, act, x_saved ? 1 : 0);
             else k_field_backward_dgrad<false><<<grid, FIELD_BWD_BLOCK, FIELD_BWD_SMEM_BYTES, st>>>(*P, m, position + 3 * c0, nullptr, d_mat + 5 * c0, act, x_saved ? 1 : 0);
@@ -565,12 +580,12 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
             else k_field_backward_scatter<false><<<gs, 256, 0, st>>>(*P, m, position + 3 * c0, nullptr, act, d_params + 9216);
         }
         LAUNCHED();
-        {
+        if (!fused) {
             ProfScope ps(K_FIELD_WGRAD, st);
             const unsigned g2 = (unsigned)std::min<int64_t>((m + 31) / 32, (int64_t)g_sm_count * 3);
             k_field_backward_wgrad<<<g2, IRIS_BLOCK, FIELD_WGRAD_SMEM_BYTES, st>>>(act, m, d_params);
+            LAUNCHED();
         }
-        LAUNCHED();
     }
     return IRIS_OK;
 }
