@@ -1,5 +1,5 @@
-// field_bwd_tc5.cuh -- EXPERIMENTAL (off by default, iris_set_option("field_backward_impl", 1)): the field adjoint's dgrad AND wgrad as ONE
-// tcgen05 kernel, so that the activations h1, h2 and the back-propagated dh2^, dh1^ never leave the SM (DESIGN.md section 9, item 1:
+// field_bwd_tc5.cuh -- the field adjoint's dgrad AND wgrad as ONE tcgen05 kernel (default whenever the forward kept the encoded inputs;
+// iris_set_option("field_backward_impl", 0) selects the two-kernel form of field.cuh), so that the activations h1, h2 and the back-propagated dh2^, dh1^ never leave the SM (DESIGN.md section 9, item 1:
 // the two-kernel form moves 1.6 KB/sample through HBM, this one 0.26 KB).  The grid scatter stays k_field_backward_scatter.
 //
 // One CTA = 128 threads = one 128-sample tile, thread i owns sample i (as in field_tc5.cuh).  Per tile, six MMA rounds:
@@ -11,7 +11,8 @@
 // dh^ is normalised per sample by a power of two s_i (the grid gradient needs the small samples' relative precision); dh~ = dh^ *
 // s_i / S is the wgrad operand, S = one power of two per CTA that bounds every |dy| of the CTA's samples (from max|d_mat| / 4), so
 // dh~ fits fp16 and the accumulators are rescaled by S exactly before they leave.  Operand mechanics verified by
-// tools/probe/umma_mn_probe.cu.  NOT yet validated end to end: the host only launches it behind the option.
+// tools/probe/umma_mn_probe.cu; tests/test_gpu_parity.py::test_fused_tcgen05_adjoint_equals_two_kernel_adjoint checks it against the
+// two-kernel form (1e-6 of max), and the oracle / golden gradient tests run through it.
 #pragma once
 #include "field_tc5.cuh"
 

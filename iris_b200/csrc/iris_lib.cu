@@ -555,7 +555,7 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
         if (x_saved) act.X = x_saved + 64 * c0;        // encoded inputs kept by the forward pass: not recomputed, not copied
         const int64_t tiles = (m + FIELD_BWD_BLOCK - 1) / FIELD_BWD_BLOCK;
         const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * (512 / FIELD_BWD_BLOCK));
-        const bool fused = g_field_bwd_impl == 1 && x_saved != nullptr;          // EXPERIMENTAL one-kernel dgrad + wgrad on tcgen05 (field_bwd_tc5.cuh)
+        const bool fused = g_field_bwd_impl == 1 && x_saved != nullptr;          // one-kernel dgrad + wgrad on tcgen05 (field_bwd_tc5.cuh)
         if (fused) {
             static bool fattr[64] = {false};
             if (!fattr[cur_dev & 63]) {
