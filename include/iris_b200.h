@@ -265,7 +265,7 @@ int iris_set_option(const char *name, int value);
 
 /* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its own stream.
  * iris_profile_read synchronises the pending events and returns the launch count and the summed duration of one
- * kernel class (ids 0..18, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */
+ * kernel class (ids 0..19, names from iris_profile_name; NULL past the end).  Used for bench.py's roofline line. */
 int iris_profile_enable(int on);
 const char *iris_profile_name(int kernel_id);
 int iris_profile_read(int kernel_id, int64_t *launches, double *total_ms, int reset);

@@ -46,8 +46,8 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
-enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_SINGLE_GEN, K_TRACE_QUEUE, K_SINGLE_SHADE, K_BAKE_GEN, K_BAKE_SHADE, K_COUNT };
-static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish", "k_single_gen", "k_trace_queue", "k_single_shade", "k_bake_gen", "k_bake_shade"};
+enum KernelId { K_INTERSECT = 0, K_BAKE_DIFFUSE, K_BAKE_SPECULAR, K_PRIMARY, K_FIELD_FORWARD, K_BOUNCE_SINGLE, K_SINGLE_BACKWARD, K_FIELD_BACKWARD, K_FIELD_WGRAD, K_FIELD_SCATTER, K_WAVE_INIT, K_WAVE_A, K_WAVE_B, K_WAVE_FINISH, K_SINGLE_GEN, K_TRACE_QUEUE, K_SINGLE_SHADE, K_BAKE_GEN, K_BAKE_SHADE, K_FIELD_BACKWARD_TC5, K_COUNT };
+static const char *g_kernel_names[K_COUNT] = {"k_intersect", "k_bake<0>", "k_bake<1>", "k_primary", "k_field_forward", "k_bounce_single", "k_single_backward", "k_field_backward_dgrad", "k_field_backward_wgrad", "k_field_backward_scatter", "k_wave_init", "k_wave_bounce_a", "k_wave_bounce_b", "k_wave_finish", "k_single_gen", "k_trace_queue", "k_single_shade", "k_bake_gen", "k_bake_shade", "k_field_backward_tc5"};
 struct ProfSpan { int id; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
@@ -563,7 +563,7 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
                 CUDA_TRY(cudaFuncSetAttribute(k_field_backward_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT5_SMEM_BYTES));
                 fattr[cur_dev & 63] = true;
             }
-            ProfScope ps(K_FIELD_BACKWARD, st);
+            ProfScope ps(K_FIELD_BACKWARD_TC5, st);
             const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * 2);
             if (r5) k_field_backward_tc5<true><<<gf, TC5_ROWS, BT5_SMEM_BYTES, st>>>(*P, m, r5 + c0, d_mat + 5 * c0, act.X, act.dx, act.s, d_params);
             else k_field_backward_tc5<false><<<gf, TC5_ROWS, BT5_SMEM_BYTES, st>>>(*P, m, nullptr, d_mat + 5 * c0, act.X, act.dx, act.s, d_params);
