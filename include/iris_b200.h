@@ -39,6 +39,10 @@ typedef enum IrisStatus {
 const char *iris_last_error(void);
 /* "iris_b200 <version> sm_100a" */
 const char *iris_version(void);
+/* Binding handshake: what = 0 -> IRIS_ABI_VERSION, 1 -> sizeof(IrisShadeParams), 2 -> sizeof(IrisSampler), 3 -> sizeof(IrisSceneStats),
+ * anything else -> -1.  A binding that mirrors the structs by hand (ctypes, cgo) compares these before the first call. */
+#define IRIS_ABI_VERSION 2
+int64_t iris_abi_info(int what);
 
 /* ------------------------------------------------------------------------------------------------
  * Scene: one triangle mesh + 8-wide compressed BVH resident in HBM.
@@ -124,6 +128,18 @@ int iris_sampler_fill(uint64_t seed, uint64_t lane_offset, int64_t n, int32_t di
 int iris_bake(const IrisScene *scene, const IrisShadeParams *params, int mode, float roughness,
               const float *position, const float *normal, const float *wo, int64_t n_pixels, int32_t spp,
               const IrisSampler *sampler, float *out0, float *out1, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BSDF samplers, one lane per row -- BaseBRDF.sample_diffuse (mode 0, model/brdf.py:78-88), .sample_specular (mode 1, :112-136) and
+ * .sample_brdf (mode 2, :177-210) for callers that drive the sampling loop themselves (bake_shading.py:113-114,173-177); the fused
+ * estimators inline the same code.  u (n,u_stride): mode 0/1 read columns 0,1 (sample2); mode 2 reads column 0 (sample1) and 1,2.
+ * wo, normal (n,3); mat (n,5) = albedo rgb, roughness, metallic (mode 2; mode 1: NULL = the scalar `roughness` level, else mat[:,3]).
+ * Out: wi (n,3); pdf (n); w0 (n,3) = ones | F0*fac | brdf/pdf; w1 (n,3) = F1*fac (mode 1).  pdf / w0 / w1 may be NULL.
+ * sin / cos / asin / acos are the library's own fixed polynomial definitions (csrc/trig.cuh), so a sampled direction is a
+ * reproducible function of its inputs, identical to the one the fused estimators trace.
+ * ---------------------------------------------------------------------------------------------- */
+int iris_bsdf_sample(int mode, const float *u, int32_t u_stride, const float *wo, const float *normal, const float *mat, float roughness,
+                     int64_t n, float *wi, float *pdf, float *w0, float *w1, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BRDF field -- NGPBRDF.forward (model/brdf.py:243-260): mat (n,5) = albedo rgb, roughness, metallic.

@@ -70,6 +70,8 @@ PROTOTYPES = {
     "iris_brdf_shading_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
     "iris_crf_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "iris_crf_backward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "iris_bsdf_sample": (ctypes.c_int, [ctypes.c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "iris_abi_info": (c_i64, [ctypes.c_int]),
     "iris_launch_count": (c_i64, []),
     "iris_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "iris_profile_enable": (ctypes.c_int, [ctypes.c_int]),
@@ -78,13 +80,17 @@ PROTOTYPES = {
 }
 
 _LIB = None
+ABI_VERSION = 2          # include/iris_b200.h: IRIS_ABI_VERSION
 
 
 def lib():
-    """Load libiris_b200.so (building it with nvcc first if the in-tree .so is missing and nvcc exists)."""
+    """Load libiris_b200.so.  With nvcc on PATH the (mtime-checked) in-tree build runs first, so an edited source never meets a
+    stale binary; without nvcc a missing library is an error.  The library's ABI version and struct sizes are checked against the
+    ctypes mirrors above: a drifted layout raises instead of corrupting device pointers."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
+        import shutil
+        if "IRIS_B200_LIB" not in os.environ and (shutil.which("nvcc") or not os.path.exists(LIB_PATH)):
             from . import build as _build
             _build.build()
         L = ctypes.CDLL(LIB_PATH)
@@ -92,6 +98,11 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        got = [L.iris_abi_info(k) for k in range(4)]
+        want = [ABI_VERSION, ctypes.sizeof(IrisShadeParams), ctypes.sizeof(IrisSampler), ctypes.sizeof(IrisSceneStats)]
+        if got != want:
+            raise RuntimeError("iris_b200: %s does not match this binding (abi/struct sizes %r, expected %r) -- rebuild with python iris_b200/build.py --force"
+                               % (LIB_PATH, got, want))
         _LIB = L
     return _LIB
 

@@ -199,6 +199,24 @@ def bake(scene, tables, mode, roughness, position, normal, wo, spp, sampler):
     return out0 if mode == 0 else (out0, out1)
 
 
+def bsdf_sample(mode, u, wo, normal, mat=None, roughness=0.0):
+    """BaseBRDF.sample_diffuse (mode 0) / sample_specular (1) / sample_brdf (2), model/brdf.py:78-210, one lane per row.
+    u (n,2) [mode 2: (n,3) = sample1 | sample2]; returns wi (n,3), pdf (n), w0 (n,3), w1 (n,3) [mode 1 only, else None]."""
+    u = u.contiguous().float()
+    normal = normal.contiguous().float()
+    wo = None if wo is None else wo.contiguous().float()
+    mat = None if mat is None else mat.contiguous().float()
+    n, dev = normal.shape[0], normal.device
+    wi = torch.empty(n, 3, device=dev)
+    pdf = torch.empty(n, device=dev)
+    w0 = torch.empty(n, 3, device=dev)
+    w1 = torch.empty(n, 3, device=dev) if mode == 1 else None
+    with torch.cuda.device(dev):
+        C.check(C.lib().iris_bsdf_sample(int(mode), C.ptr(u), u.shape[1] if u.dim() == 2 else 0, C.ptr(wo), C.ptr(normal), C.ptr(mat), float(roughness), n,
+                                         C.ptr(wi), C.ptr(pdf), C.ptr(w0), C.ptr(w1), C.stream_ptr()))
+    return wi, pdf, w0, w1
+
+
 def field_forward(tables, position, want_encoded=False):
     """NGPBRDF.forward: mat (n,5).  want_encoded: also return the (n,64) fp16 hash-grid features for field_backward(encoded=...)."""
     position = position.contiguous().float()

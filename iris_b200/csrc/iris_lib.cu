@@ -18,6 +18,7 @@
 #include "shade_maps.cuh"
 #include "slf_bake.cuh"
 #include "emitter_extract.cuh"
+#include "bsdf_api.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -199,7 +200,16 @@ done:
 extern "C" {
 
 const char *iris_last_error(void) { return g_err.c_str(); }
-const char *iris_version(void) { return "iris_b200 0.1 sm_100a"; }
+const char *iris_version(void) { return "iris_b200 0.2 sm_100a"; }
+int64_t iris_abi_info(int what) {
+    switch (what) {
+    case 0: return IRIS_ABI_VERSION;
+    case 1: return (int64_t)sizeof(IrisShadeParams);
+    case 2: return (int64_t)sizeof(IrisSampler);
+    case 3: return (int64_t)sizeof(IrisSceneStats);
+    default: return -1;
+    }
+}
 int64_t iris_launch_count(void) { return g_launches.load(); }
 
 int iris_set_option(const char *name, int value) {
@@ -883,6 +893,21 @@ int iris_trace_indirect(const IrisScene *s, const IrisShadeParams *P, const floa
         ProfScope ps(K_WAVE_FINISH, st);
         k_wave_finish<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n, 1, W, L, nullptr);
     }
+    LAUNCHED();
+    return IRIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ BSDF samplers (model/brdf.py:78-210)
+int iris_bsdf_sample(int mode, const float *u, int32_t u_stride, const float *wo, const float *normal, const float *mat, float roughness, int64_t n,
+                     float *wi, float *pdf, float *w0, float *w1, void *stream) {
+    if (mode < 0 || mode > 2) return fail(IRIS_ERR_INVALID, "mode must be 0 (sample_diffuse), 1 (sample_specular) or 2 (sample_brdf)");
+    if (n < 0 || u_stride < (mode == 2 ? 3 : 2)) return fail(IRIS_ERR_INVALID, "bad bsdf_sample arguments");
+    if (n == 0) return IRIS_OK;
+    if (!u || !normal || !wi || (mode >= 1 && !wo) || (mode == 2 && !mat)) return fail(IRIS_ERR_INVALID, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) k_bsdf_sample<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(u, u_stride, wo, normal, mat, roughness, n, wi, pdf, w0, w1);
+    else if (mode == 1) k_bsdf_sample<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(u, u_stride, wo, normal, mat, roughness, n, wi, pdf, w0, w1);
+    else k_bsdf_sample<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(u, u_stride, wo, normal, mat, roughness, n, wi, pdf, w0, w1);
     LAUNCHED();
     return IRIS_OK;
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(IRIS_SORT_BLOCK) k_bake(SceneView S, IrisShade
             wi = specular_sampler(u.x, u.y, roughness, wo, nr);
             specular_weights(wi, wo, nr, roughness, w0, w1);
         }
-        org = mk3(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z);
+        org = ray_origin(x, wi);
     }
     const Hit h = block_sorted_trace<false>(S, sort, org, wi, in_range, __int_as_float(0x7f800000), -1);
     if (in_range) {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK, 8) k_bake_persistent(SceneView S, 
                         wi = specular_sampler(u.x, u.y, roughness, wo, nr);
                         specular_weights(wi, wo, nr, roughness, w0, w1);
                     }
-                    trav_init(T, mk3(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z), wi,
+                    trav_init(T, ray_origin(x, wi), wi,
                               __int_as_float(0x7f800000), -1, 0);
                 }
             }
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_bake_gen(IrisSampler smp, float 
     const f3 x = ld3(position, pix), nr = ld3(normal, pix);
     const float4 u = sample4(smp, i, 0);
     const f3 wi = MODE == 0 ? diffuse_sampler(u.x, u.y, nr) : specular_sampler(u.x, u.y, roughness, ld3(wo_in, pix), nr);
-    ro[j] = make_float4(x.x + IRIS_RAY_EPSILON * wi.x, x.y + IRIS_RAY_EPSILON * wi.y, x.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
+    ro[j] = ray4(ray_origin(x, wi), __int_as_float(0x7f800000));
     rd[j] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
 }
 
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
             float pdf_e;
             int32_t e, face;
             sample_emitter(P, ua.z, ua.w, ub.x, x0, wi, pdf_e, e, face);
-            const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+            const f3 org = ray_origin(x0, wi);
             f3 v0, e1, e2;
             emitter_triangle(P, e, v0, e1, e2);
             float tl, bu, bv;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
         float pdf_b;
         BrdfJac J;
         sample_brdf<REC == 2>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
-        ro_b = make_float4(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
+        ro_b = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
         rd_b = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
         st[j] = make_float4(L_nee.x, L_nee.y, L_nee.z, pdf_b);
         st[nc + j] = make_float4(wb.x, wb.y, wb.z, __int_as_float(e_nee));
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
                 float pdf_e;
                 int32_t e, face;
                 sample_emitter(P, ua.z, ua.w, ub.x, x0, wi, pdf_e, e, face);
-                const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+                const f3 org = ray_origin(x0, wi);
                 f3 v0, e1, e2;
                 emitter_triangle(P, e, v0, e1, e2);
                 float tl, bu, bv;
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
                 float pdf_b;
                 BrdfJac J;
                 sample_brdf<RECORD>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
-                const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+                const f3 org = ray_origin(x0, wi);
                 const Hit h = trace_closest_shared(S, org, wi);
                 f3 hp, hn;
                 hit_surface(S, h, wi, hp, hn);

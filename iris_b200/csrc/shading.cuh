@@ -6,6 +6,7 @@
 #include "../../include/iris_b200.h"
 #include "common.cuh"
 #include "traverse.cuh"
+#include "trig.cuh"
 
 // ------------------------------------------------------------------------------------------------ samples
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -41,25 +42,29 @@ __device__ __forceinline__ float4 sample4(const IrisSampler &s, int64_t lane, in
 }
 
 // ------------------------------------------------------------------------------------------------ frames + samplers
+// Everything between the uniforms and a sampled direction is one IEEE rounding per operation, in the order of the reference's
+// ATen chain (products rounded before they are summed; the 1x3 @ 3x3 frame change accumulates left to right), with the
+// transcendentals of trig.cuh: the CPU checker restates the same sequence, so secondary rays agree bit for bit.
 // utils/ops.py:12-30
 __device__ __forceinline__ void normal_space(f3 n, f3 &t, f3 &b) {
     const f3 a = fabsf(n.x) <= 0.1f ? mk3(1.f, 0.f, 0.f) : mk3(0.f, 1.f, 0.f);
-    t = normalize_nf(cross(a, n));
-    b = cross(n, t);
+    t = normalize_nf(xcross(a, n));
+    b = xcross(n, t);
 }
 // utils/ops.py:32-44 followed by the frame change of model/brdf.py:32-33
 __device__ __noinline__ f3 sphere_to_world(float theta, float phi, f3 n) {
     float st, ct, sp, cp;
-    sincosf(theta, &st, &ct);
-    sincosf(phi, &sp, &cp);
-    const f3 l = normalize_nf(mk3(st * cp, st * sp, ct));
+    iris_sincosf(theta, st, ct);
+    iris_sincosf(phi, sp, cp);
+    const f3 l = normalize_nf(mk3(xmul(st, cp), xmul(st, sp), ct));
     f3 t, b;
     normal_space(n, t, b);
-    return l.x * t + l.y * b + l.z * n;
+    return mk3(xadd(xadd(xmul(l.x, t.x), xmul(l.y, b.x)), xmul(l.z, n.x)), xadd(xadd(xmul(l.x, t.y), xmul(l.y, b.y)), xmul(l.z, n.y)),
+               xadd(xadd(xmul(l.x, t.z), xmul(l.y, b.z)), xmul(l.z, n.z)));
 }
 // model/brdf.py:20-34
 __device__ __forceinline__ f3 diffuse_sampler(float u0, float u1, f3 n) {
-    return sphere_to_world(asinf(sqrtf(u0)), (IRIS_PI * 2.f) * u1, n);
+    return sphere_to_world(iris_asinf(__fsqrt_rn(u0)), xmul(IRIS_PI * 2.f, u1), n);
 }
 // model/brdf.py:36-59
 __device__ __forceinline__ f3 specular_sampler(float u0, float u1, float roughness, f3 wo, f3 n) {
@@ -67,8 +72,14 @@ __device__ __forceinline__ f3 specular_sampler(float u0, float u1, float roughne
     // order, or the sampled lobe direction moves by whole quanta of acos near 1
     const float alpha = xmul(roughness, roughness);
     const float c2 = __fdiv_rn(xsub(1.f, u0), xadd(xmul(u0, xsub(xmul(alpha, alpha), 1.f)), 1.f));
-    const f3 wh = sphere_to_world(acosf(sqrtf(c2)), (2.f * IRIS_PI) * u1, n);
-    return normalize_nf((2.f * dot(wo, wh)) * wh - wo);
+    const f3 wh = sphere_to_world(iris_acosf(__fsqrt_rn(c2)), xmul(2.f * IRIS_PI, u1), n);
+    const float d2 = xmul(2.f, xdot(wo, wh));
+    return normalize_nf(mk3(xsub(xmul(d2, wh.x), wo.x), xsub(xmul(d2, wh.y), wo.y), xsub(xmul(d2, wh.z), wo.z)));
+}
+// origin of a secondary ray: x + RayEpsilon * wi, product rounded before the sum (utils/path_tracing.py:97,260,286,365,391,443,471)
+__device__ __forceinline__ float4 ray4(f3 o, float w) { return make_float4(o.x, o.y, o.z, w); }
+__device__ __forceinline__ f3 ray_origin(f3 x, f3 wi) {
+    return mk3(xadd(x.x, xmul(IRIS_RAY_EPSILON, wi.x)), xadd(x.y, xmul(IRIS_RAY_EPSILON, wi.y)), xadd(x.z, xmul(IRIS_RAY_EPSILON, wi.z)));
 }
 
 // ------------------------------------------------------------------------------------------------ BSDF
@@ -213,12 +224,14 @@ __device__ __forceinline__ void sample_emitter(const IrisShadeParams &P, float u
         if (__ldg(P.emitter_cdf + mid) < u) lo = mid + 1; else hi = mid;
     }
     e = min(lo, P.n_emitters - 1);
-    const float xi = sqrtf(u2x);
-    const float bu = 1.f - xi, bv = xi * u2y, bw = 1.f - bu - bv;
+    const float xi = __fsqrt_rn(u2x);
+    const float bu = xsub(1.f, xi), bv = xmul(xi, u2y), bw = xsub(xsub(1.f, bu), bv);
     const float *V = P.emitter_vertices + 9 * (int64_t)e;
-    const f3 p1 = mk3(__ldg(V + 0) * bu + __ldg(V + 3) * bv + __ldg(V + 6) * bw, __ldg(V + 1) * bu + __ldg(V + 4) * bv + __ldg(V + 7) * bw,
-                      __ldg(V + 2) * bu + __ldg(V + 5) * bv + __ldg(V + 8) * bw);
-    wi = normalize_nf(p1 - x);
+    // p1 = v0*u + v1*v + v2*w, products rounded, summed left to right (model/emitter.py:246-247)
+    const f3 p1 = mk3(xadd(xadd(xmul(__ldg(V + 0), bu), xmul(__ldg(V + 3), bv)), xmul(__ldg(V + 6), bw)),
+                      xadd(xadd(xmul(__ldg(V + 1), bu), xmul(__ldg(V + 4), bv)), xmul(__ldg(V + 7), bw)),
+                      xadd(xadd(xmul(__ldg(V + 2), bu), xmul(__ldg(V + 5), bv)), xmul(__ldg(V + 8), bw)));
+    wi = normalize_nf(mk3(xsub(p1.x, x.x), xsub(p1.y, x.y), xsub(p1.z, x.z)));
     pdf = emitter_pdf_area(P, e);
     face = __ldg(P.face_of_emitter + e);
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_a(SceneView S, IrisS
             float pdf_e;
             int32_t e, face;
             sample_emitter(P, u[0], u[1], u[2], x0, wl, pdf_e, e, face);
-            const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wl.x, x0.y + IRIS_RAY_EPSILON * wl.y, x0.z + IRIS_RAY_EPSILON * wl.z);
+            const f3 org = ray_origin(x0, wl);
             f3 v0, e1, e2;
             emitter_triangle(P, e, v0, e1, e2);
             float tl, bu, bv;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_a(SceneView S, IrisS
         W.S7[i] = make_float4(w0, w0, w0, 0.f);
         W.S8[i] = make_float4(w1, w1, w1, 0.f);
     }
-    const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z);
+    const f3 org = ray_origin(x0, wi);
     const Hit h = trace_closest_shared(S, org, wi);
     f3 hp, hn;
     hit_surface(S, h, wi, hp, hn);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, Iris
             float pdf_e;
             int32_t e, face;
             sample_emitter(P, u[0], u[1], u[2], x0, wl, pdf_e, e, face);
-            const f3 org = mk3(x0.x + IRIS_RAY_EPSILON * wl.x, x0.y + IRIS_RAY_EPSILON * wl.y, x0.z + IRIS_RAY_EPSILON * wl.z);
+            const f3 org = ray_origin(x0, wl);
             f3 v0, e1, e2;
             emitter_triangle(P, e, v0, e1, e2);
             float tl, bu, bv;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, Iris
     }
     W.RO[i] = ro_s;
     W.RD[i] = rd_s;
-    W.RO[n + i] = make_float4(x0.x + IRIS_RAY_EPSILON * wi.x, x0.y + IRIS_RAY_EPSILON * wi.y, x0.z + IRIS_RAY_EPSILON * wi.z, __int_as_float(0x7f800000));
+    W.RO[n + i] = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
     W.RD[n + i] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
     W.PN[i] = make_float4(pend.x, pend.y, pend.z, bpdf);
 }

@@ -1,7 +1,10 @@
 """BSDF classes with the reference's interface (model/brdf.py).
 
-`BaseBRDF` carries the GGX / Lambert samplers and evaluators with the reference's signatures (batched torch ops, used by
-callers outside the fused kernels); `NGPBRDF(voxel_min, voxel_max)` is the hash-grid + MLP material field whose forward and
+`BaseBRDF` carries the GGX / Lambert samplers and evaluators with the reference's signatures for callers that drive the
+sampling loop themselves (bake_shading.py:113-114,173-177): on CUDA tensors `sample_diffuse` / `sample_specular` and the
+gradient-free `sample_brdf` run on the library's kernel (iris_bsdf_sample -- the same device code, and the same fixed
+sin / cos / asin / acos definitions, as the fused estimators); the evaluators, and `sample_brdf` when the material carries
+gradients, are batched torch expressions; `NGPBRDF(voxel_min, voxel_max)` is the hash-grid + MLP material field whose forward and
 adjoint run on the CUDA path (iris_field_forward / iris_field_backward) and whose state_dict key is the reference's
 `mlp.params` (one flat fp32 vector [MLP 9216 | grid 27 954 112], tiny-cuda-nn layout)."""
 from __future__ import annotations
@@ -70,6 +73,10 @@ class BaseBRDF(nn.Module):
         return pdf.expand(len(wi), 3), pdf
 
     def sample_diffuse(self, sample2, normal):
+        if normal.is_cuda:
+            from .. import core
+            wi, pdf, w0, _ = core.bsdf_sample(0, sample2.reshape(-1, 2), None, normal.reshape(-1, 3))
+            return wi, pdf[:, None], w0
         wi = diffuse_sampler(sample2, normal)
         return wi, (normal * wi).sum(-1, keepdim=True).relu() / math.pi, torch.ones_like(normal)
 
@@ -81,6 +88,16 @@ class BaseBRDF(nn.Module):
         return base * (1 - x), base * x, D.detach() / (4 * VoH.clamp_min(1e-4)) * NoH
 
     def sample_specular(self, sample2, wo, normal, roughness):
+        if normal.is_cuda and not (torch.is_tensor(roughness) and roughness.requires_grad):
+            from .. import core
+            per_lane = torch.is_tensor(roughness) and roughness.numel() > 1      # (B,1) tensor, or the scalar level of bake_shading.py:147
+            mat = None
+            if per_lane:
+                mat = torch.zeros(normal.shape[0], 5, device=normal.device)
+                mat[:, 3] = roughness.reshape(-1)
+            wi, pdf, w0, w1 = core.bsdf_sample(1, sample2.reshape(-1, 2), wo.reshape(-1, 3), normal.reshape(-1, 3), mat=mat,
+                                               roughness=0.0 if per_lane else float(roughness))
+            return wi, pdf[:, None], w0[:, :1], w1[:, :1]
         wi = specular_sampler(sample2, roughness, wo, normal)
         NoL, NoV, VoH, NoH = _cosines(wi, wo, normal)
         pdf = _D(NoH, roughness).detach() / (4 * VoH.clamp_min(1e-4)) * NoH
@@ -98,6 +115,12 @@ class BaseBRDF(nn.Module):
         return a * (1 - m) / math.pi * NoL + D * _G(NoV, NoL, r) * F / 4.0 * NoL, pdf
 
     def sample_brdf(self, sample1, sample2, wo, normal, mat):
+        if normal.is_cuda and not any(v.requires_grad for v in mat.values()):
+            from .. import core
+            u = torch.cat([sample1.reshape(-1, 1), sample2.reshape(-1, 2)], 1)
+            m = torch.cat([mat["albedo"], mat["roughness"], mat["metallic"]], -1)
+            wi, pdf, w, _ = core.bsdf_sample(2, u, wo.reshape(-1, 3), normal.reshape(-1, 3), mat=m)
+            return wi, pdf[:, None], w
         pick_diffuse = (sample1 > 0.5)[:, None]
         wi = torch.where(pick_diffuse, diffuse_sampler(sample2, normal), specular_sampler(sample2, mat["roughness"], wo, normal))
         brdf, pdf = self.eval_brdf(wi, wo, normal, mat)

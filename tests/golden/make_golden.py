@@ -85,46 +85,79 @@ def slf_golden():
     print("slf.npz", {k: getattr(v, "shape", v) for k, v in g.items()}, "cells", len(g["count"]))
 
 
+def small_case(shared_trig):
+    """Every estimator on the `small` case.  shared_trig: run the reference with torch.sin / cos / asin / acos replaced by the
+    fixed polynomial definitions of oracle/trig.c (the ones the CUDA kernels use) -- "the reference on this libm"."""
+    import contextlib
+    from oracle import trig as T
+    ctx = T.patched_torch() if shared_trig else contextlib.nullcontext()
+    with ctx:
+        c = cases.build("small")
+        osc = OracleScene(c["sc"].vertices, c["sc"].faces)
+        r = torch.as_tensor(c["rays"])
+        U = torch.as_tensor(c["U"])
+        g = single_with_grads(c, osc)
+        em = RH.make_emitter(c["sc"], c["H"], learn=False)
+        mat = RH.make_material(c["sc"], c["params"])
+        pos, nrm, uv, tri, valid = osc.ray_intersect(r[:, 0:3], r[:, 3:6])
+        raw = osc.intersect_raw(c["rays"][:, 0:3], c["rays"][:, 3:6], "brute")
+        g.update(prim=raw["prim"], t=raw["t"], uv=raw["uv"], p=raw["p"], n=raw["n"])
+        g["L_full"] = RH.run_full(osc, em, mat, c["rays"], c["spp"], c["depth"], U).numpy()
+        tri2 = tri.clone()
+        tri2[5] = -1
+        tri2[100] = -1
+        Ud = U[:, :2 + 6 * c["depth"]]
+        g["det_diff"] = RH.run_det_diff(osc, em, mat, pos, r[:, 3:6], nrm, tri2, c["spp"], c["depth"], Ud).numpy()
+        levels = torch.linspace(0.02, 1.0, 6)
+        for i in (0, 2, 5):
+            a0, a1 = RH.run_det_spec(osc, em, mat, levels[i], pos, r[:, 3:6], nrm, tri2, c["spp"], c["depth"], Ud)
+            g["det_spec0_%d" % i], g["det_spec1_%d" % i] = a0.numpy(), a1.numpy()
+        g["bake_diff"] = RH.run_bake(osc, em, pos, nrm, -r[:, 3:6], c["spp"], U[:, :2]).numpy()
+        for i in range(6):
+            a0, a1 = RH.run_bake(osc, em, pos, nrm, -r[:, 3:6], c["spp"], U[:, :2], level=levels[i])
+            g["bake_spec0_%d" % i], g["bake_spec1_%d" % i] = a0.numpy(), a1.numpy()
+        # the sampled directions themselves (BaseBRDF.sample_diffuse / sample_specular / sample_brdf on the pixel-centre hits)
+        n = len(pos)
+        brdf = RH.load_reference()["brdf"].BaseBRDF()
+        u3 = U[:n, 5:8].contiguous()
+        wo = -r[:, 3:6]
+        g["dir_diffuse"] = brdf.sample_diffuse(u3[:, 1:3], nrm)[0].numpy()
+        g["dir_specular"] = brdf.sample_specular(u3[:, 1:3], wo, nrm, levels[2])[0].numpy()
+        with torch.no_grad():
+            m = mat(pos)
+            wi, pdf, w = brdf.sample_brdf(u3[:, 0], u3[:, 1:3], wo, nrm, m)
+        g["dir_brdf"], g["dir_brdf_pdf"], g["dir_brdf_w"] = wi.numpy(), pdf.numpy(), w.numpy()
+    return g
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "shading":
         return shading_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "slf":
         return slf_golden()
-    out = {}
-    # ---------------- small: every estimator
-    c = cases.build("small")
-    osc = OracleScene(c["sc"].vertices, c["sc"].faces)
-    r = torch.as_tensor(c["rays"])
-    U = torch.as_tensor(c["U"])
-    g = single_with_grads(c, osc)
-    em = RH.make_emitter(c["sc"], c["H"], learn=False)
-    mat = RH.make_material(c["sc"], c["params"])
-    pos, nrm, uv, tri, valid = osc.ray_intersect(r[:, 0:3], r[:, 3:6])
-    raw = osc.intersect_raw(c["rays"][:, 0:3], c["rays"][:, 3:6], "brute")
-    g.update(prim=raw["prim"], t=raw["t"], uv=raw["uv"], p=raw["p"], n=raw["n"])
-    g["L_full"] = RH.run_full(osc, em, mat, c["rays"], c["spp"], c["depth"], U).numpy()
-    tri2 = tri.clone()
-    tri2[5] = -1
-    tri2[100] = -1
-    Ud = U[:, :2 + 6 * c["depth"]]
-    g["det_diff"] = RH.run_det_diff(osc, em, mat, pos, r[:, 3:6], nrm, tri2, c["spp"], c["depth"], Ud).numpy()
-    levels = torch.linspace(0.02, 1.0, 6)
-    for i in (0, 2, 5):
-        a0, a1 = RH.run_det_spec(osc, em, mat, levels[i], pos, r[:, 3:6], nrm, tri2, c["spp"], c["depth"], Ud)
-        g["det_spec0_%d" % i], g["det_spec1_%d" % i] = a0.numpy(), a1.numpy()
-    g["bake_diff"] = RH.run_bake(osc, em, pos, nrm, -r[:, 3:6], c["spp"], U[:, :2]).numpy()
-    for i in range(6):
-        a0, a1 = RH.run_bake(osc, em, pos, nrm, -r[:, 3:6], c["spp"], U[:, :2], level=levels[i])
-        g["bake_spec0_%d" % i], g["bake_spec1_%d" % i] = a0.numpy(), a1.numpy()
-    np.savez_compressed(os.path.join(HERE, "small.npz"), **g)
-    print("small.npz", {k: v.shape for k, v in g.items()})
+    # ---------------- small: every estimator, with the reference on torch's own libm and on the shared polynomial definitions
+    for tag, st in (("small", False), ("small_st", True)):
+        if len(sys.argv) > 1 and sys.argv[1] == "c1":
+            break
+        g = small_case(st)
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **g)
+        print(tag + ".npz", {k: v.shape for k, v in g.items()})
+    if len(sys.argv) > 1 and sys.argv[1] == "small":
+        return
 
     # ---------------- C1: Cornell 64x64 spp 16, path_tracing_single fwd + bwd (BASELINE.json configs[0])
+    from oracle import trig as T
     c = cases.build("c1")
     osc = OracleScene(c["sc"].vertices, c["sc"].faces)
     g = single_with_grads(c, osc)
     np.savez_compressed(os.path.join(HERE, "c1.npz"), **g)
     print("c1.npz", {k: v.shape for k, v in g.items()})
+    with T.patched_torch():
+        g = single_with_grads(c, osc)
+    np.savez_compressed(os.path.join(HERE, "c1_st.npz"), **g)
+    print("c1_st.npz", {k: v.shape for k, v in g.items()})
+    if len(sys.argv) > 1 and sys.argv[1] == "c1":
+        return
     shading_golden()
     slf_golden()
 

@@ -40,7 +40,10 @@ def small():
     c["em"] = E.Emitter(sc.emitter_dict(), sc.slf_dict(c["H"]))
     vmin, vmax = sc.voxel_bounds()
     c["mat_fn"] = lambda x: OF.material(x, c["params"], vmin, vmax)
-    c["gold"] = np.load(os.path.join(GOLD, "small.npz"))
+    # the reference's own outputs, with torch.sin / cos / asin / acos replaced by the fixed definitions the kernels use
+    # (tests/golden/make_golden.py); `gold_libm` is the same run on torch's libm, kept to state the libm-vs-libm delta
+    c["gold"] = np.load(os.path.join(GOLD, "small_st.npz"))
+    c["gold_libm"] = np.load(os.path.join(GOLD, "small.npz"))
     return c
 
 
@@ -221,7 +224,7 @@ def test_c1_forward_backward_golden():
     from iris_b200 import core
     c = cases.build("c1")
     sc = c["sc"]
-    g = np.load(os.path.join(GOLD, "c1.npz"))
+    g = np.load(os.path.join(GOLD, "c1_st.npz"))
     scene = core.Scene(sc.vertices, sc.faces, 0)
     tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(c["H"]), c["params"], sc.voxel_bounds())
     U = torch.as_tensor(c["U"][:, :8]).to(dev)
@@ -360,18 +363,25 @@ def test_wavefront_estimators_match_golden(small):
     dev, g, spp, depth = small["dev"], small["gold"], small["spp"], small["depth"]
     r = torch.as_tensor(small["rays"])
     U = torch.as_tensor(small["U"])
-    # Beyond the first bounce the BRDF field is evaluated at SECONDARY hit points, which differ from the CPU run's by ~1e-7 (libm vs
-    # CUDA sin/cos/asin).  The finest hash level has cells of 4e-5 scene units and this fixture's grid is U(-0.5,0.5) on every level
-    # (worst case), so a fraction of lanes moves by up to ~1.5% per extra depth; depth 0 is exact to 1e-3 everywhere.
+    # Sampled directions, ray origins and therefore every secondary hit point are bit-identical to the oracle's and to the reference's
+    # run on the shared trig definitions (test_sampled_directions_bit_exact), so the hash grid (4e-5 cells, U(-0.5,0.5) on every level
+    # in this fixture: the worst case) is evaluated at the same points and the whole estimator agrees to 1e-3.  What remains are
+    # isolated fp16 rounding flips of the field (tensor-core accumulation order) on lanes next to the roughness threshold.
     L = core.path_tracing(small["scene"], small["tables"], r.to(dev), spp, 0, core.Sampler(U=U[:, :8].contiguous().to(dev)))
     with torch.no_grad():
         ref0 = E.path_tracing(small["osc"], small["em"], small["mat_fn"], r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], spp, 0, U[:, :8])
     frac, worst = _frac_close(L.cpu().numpy(), ref0.numpy())
     assert frac == 1.0, ("path_tracing depth 0", frac, worst)
     L = core.path_tracing(small["scene"], small["tables"], r.to(dev), spp, depth, core.Sampler(U=U.to(dev)))
-    frac, worst = _frac_close(L.cpu().numpy(), g["L_full"])
-    frac2, _ = _frac_close(L.cpu().numpy(), g["L_full"], rtol=3e-2)
-    assert frac >= 0.9 and frac2 >= 0.99, ("path_tracing", frac, frac2, worst)
+    with torch.no_grad():
+        ref = E.path_tracing(small["osc"], small["em"], small["mat_fn"], r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], spp, depth, U)
+    for name, want in (("oracle", ref.numpy()), ("reference golden", g["L_full"])):
+        frac, worst = _frac_close(L.cpu().numpy(), want)
+        assert frac >= 0.99 and worst < 1e-2, ("path_tracing", name, frac, worst)
+    # the same image against the reference run on torch's own libm: the reference differs from itself by this much (stated delta)
+    frac_libm, _ = _frac_close(L.cpu().numpy(), small["gold_libm"]["L_full"])
+    frac_ref, _ = _frac_close(g["L_full"], small["gold_libm"]["L_full"])
+    assert frac_libm >= frac_ref - 0.02 and frac_libm >= 0.9, (frac_libm, frac_ref)
     pos, nrm, _, tri, _ = small["osc"].ray_intersect(r[:, 0:3], r[:, 3:6])
     tri2 = tri.clone()
     tri2[5] = -1
@@ -380,8 +390,7 @@ def test_wavefront_estimators_match_golden(small):
     smp = core.Sampler(U=Ud.to(dev))
     got = core.path_tracing_det(small["scene"], small["tables"], 0, 0.0, pos.to(dev), r[:, 3:6].to(dev), nrm.to(dev), tri2.to(dev), spp, depth, smp)
     frac, worst = _frac_close(got.cpu().numpy(), g["det_diff"])
-    frac2, _ = _frac_close(got.cpu().numpy(), g["det_diff"], rtol=3e-2)
-    assert frac >= 0.9 and frac2 >= 0.99, ("det_diff", frac, frac2, worst)
+    assert frac >= 0.99 and worst < 1e-2, ("det_diff", frac, worst)
     assert float(got[5].abs().sum()) == 0.0 and float(got[100].abs().sum()) == 0.0            # pixels without a hit stay zero
     levels = torch.linspace(0.02, 1.0, 6)
     for i in (0, 2, 5):
@@ -389,8 +398,7 @@ def test_wavefront_estimators_match_golden(small):
                                        spp, depth, smp)
         for a, key in ((a0, "det_spec0_%d" % i), (a1, "det_spec1_%d" % i)):
             frac, worst = _frac_close(a.cpu().numpy(), g[key])
-            frac2, _ = _frac_close(a.cpu().numpy(), g[key], rtol=3e-2)
-            assert frac >= 0.85 and frac2 >= 0.99, (key, frac, frac2, worst)
+            assert frac >= 0.99 and worst < 1e-2, (key, frac, worst)
     # trace_indirect on its own, against the oracle
     n = len(pos)
     Ui = U[:n, :6 * depth].contiguous()
@@ -398,12 +406,60 @@ def test_wavefront_estimators_match_golden(small):
         ref = E.trace_indirect(small["osc"], small["em"], small["mat_fn"], pos, -r[:, 3:6], nrm, torch.ones(n, dtype=torch.bool), Ui, depth)
     got = core.trace_indirect(small["scene"], small["tables"], pos.to(dev), (-r[:, 3:6]).to(dev), nrm.to(dev), depth, core.Sampler(U=Ui.to(dev)))
     frac, worst = _frac_close(got.cpu().numpy(), ref.numpy())
-    assert frac >= 0.98 and worst < 3e-2, ("trace_indirect", frac, worst)
+    assert frac >= 0.99 and worst < 1e-2, ("trace_indirect", frac, worst)
     # depth 0 and empty inputs
     L0 = core.path_tracing(small["scene"], small["tables"], r[:7].to(dev), 3, 0, core.Sampler(seed=5))
     assert L0.shape == (7, 3) and torch.isfinite(L0).all()
     assert core.trace_indirect(small["scene"], small["tables"], torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev),
                                2, core.Sampler(seed=5)).shape == (0, 3)
+
+
+def test_sampled_directions_bit_exact(small):
+    """BaseBRDF.sample_diffuse / sample_specular / sample_brdf (model/brdf.py:78-210) through iris_bsdf_sample: the sampled
+    directions equal, bit for bit, the oracle's and the REFERENCE's own (its run with the shared sin/cos/asin/acos definitions,
+    golden `dir_*`); pdf and weights to 1e-5.  This is what makes every secondary ray of the estimators identical on both sides."""
+    from iris_b200 import core
+    from oracle import estimators as E
+    dev, g = small["dev"], small["gold"]
+    r = torch.as_tensor(small["rays"])
+    pos, nrm, _, tri, _ = small["osc"].ray_intersect(r[:, 0:3], r[:, 3:6])
+    n = len(pos)
+    u3 = torch.as_tensor(small["U"])[:n, 5:8].contiguous()
+    wo = -r[:, 3:6]
+    levels = torch.linspace(0.02, 1.0, 6)
+    wi, pdf, w0, _ = core.bsdf_sample(0, u3[:, 1:3].contiguous().to(dev), None, nrm.to(dev))
+    assert np.array_equal(wi.cpu().numpy(), g["dir_diffuse"])
+    wi, pdf, w0, w1 = core.bsdf_sample(1, u3[:, 1:3].contiguous().to(dev), wo.to(dev), nrm.to(dev), roughness=float(levels[2]))
+    assert np.array_equal(wi.cpu().numpy(), g["dir_specular"])
+    ref = E.sample_specular(u3[:, 1:3], wo, nrm, levels[2])
+    assert _frac_close(pdf.cpu().numpy()[:, None], ref[1].numpy(), rtol=1e-4)[0] == 1.0
+    assert _frac_close(w0.cpu().numpy()[:, :1], ref[2].numpy(), rtol=1e-4)[0] == 1.0 and _frac_close(w1.cpu().numpy()[:, :1], ref[3].numpy(), rtol=1e-4)[0] == 1.0
+    with torch.no_grad():
+        m = small["mat_fn"](pos)
+    mat = torch.cat([m["albedo"], m["roughness"], m["metallic"]], 1).contiguous()
+    wi, pdf, w0, _ = core.bsdf_sample(2, u3.to(dev), wo.to(dev), nrm.to(dev), mat=mat.to(dev))
+    assert np.array_equal(wi.cpu().numpy(), g["dir_brdf"])
+    assert _frac_close(pdf.cpu().numpy()[:, None], g["dir_brdf_pdf"], rtol=1e-4)[0] == 1.0 and _frac_close(w0.cpu().numpy(), g["dir_brdf_w"], rtol=1e-4)[0] == 1.0
+    # a larger random set against the oracle, including grazing normals and tiny roughness
+    gen = torch.Generator().manual_seed(9)
+    N = 100_000
+    u = torch.rand(N, 3, generator=gen)
+    nn = torch.nn.functional.normalize(torch.randn(N, 3, generator=gen), dim=-1)
+    ww = torch.nn.functional.normalize(torch.randn(N, 3, generator=gen), dim=-1)
+    rr = torch.rand(N, 1, generator=gen) * 0.98 + 0.02
+    rr[:1000] = 0.02
+    mat = torch.cat([torch.rand(N, 3, generator=gen), rr, torch.rand(N, 1, generator=gen)], 1)
+    wi = core.bsdf_sample(0, u[:, :2].contiguous().to(dev), None, nn.to(dev))[0]
+    assert torch.equal(wi.cpu(), E.diffuse_sampler(u[:, :2], nn))
+    wi = core.bsdf_sample(1, u[:, :2].contiguous().to(dev), ww.to(dev), nn.to(dev), mat=mat.to(dev))[0]
+    ref = E.specular_sampler(u[:, :2], rr, ww, nn)
+    same = (wi.cpu() == ref) | (wi.cpu().isnan() & ref.isnan())
+    assert same.all()
+    wi = core.bsdf_sample(2, u.to(dev), ww.to(dev), nn.to(dev), mat=mat.to(dev))[0]
+    ref = E.sample_brdf(u[:, 0], u[:, 1:3], ww, nn, {"albedo": mat[:, 0:3], "roughness": mat[:, 3:4], "metallic": mat[:, 4:5]})[0]
+    same = (wi.cpu() == ref) | (wi.cpu().isnan() & ref.isnan())
+    assert same.all()
+    assert core.bsdf_sample(0, torch.zeros(0, 2, device=dev), None, torch.zeros(0, 3, device=dev))[0].shape == (0, 3)
 
 
 def test_reference_call_surface(small, tmp_path):

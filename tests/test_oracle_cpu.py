@@ -73,7 +73,13 @@ def test_miss_and_empty():
 
 
 def test_small_golden_all_estimators(relclose):
-    g = np.load(os.path.join(GOLD, "small.npz"))
+    """The oracle against the reference's own outputs.  `small_st.npz` is the reference run with torch.sin / cos / asin / acos
+    replaced by the fixed polynomial definitions of oracle/trig.c (the ones the oracle and the CUDA kernels use): every estimator
+    agrees to 1e-5 on every pixel.  `small.npz` is the same run on torch's own libm (Sleef): estimators whose secondary hit points
+    feed the hash grid (4e-5 cells, U(-0.5,0.5) on every level in this fixture) move with the last bit of a sampled direction --
+    that libm-vs-libm delta of the REFERENCE ITSELF is asserted below so that it stays a stated number."""
+    g = np.load(os.path.join(GOLD, "small_st.npz"))
+    g_libm = np.load(os.path.join(GOLD, "small.npz"))
     c, osc, em, p, mat_fn, r, U = _setup("small")
     raw = osc.intersect_raw(c["rays"][:, 0:3], c["rays"][:, 3:6], "bvh")
     assert (raw["prim"] == g["prim"]).all() and (raw["t"] == g["t"]).all()
@@ -101,15 +107,61 @@ def test_small_golden_all_estimators(relclose):
     for k, v in checks.items():
         frac, worst = relclose(v.numpy(), g[k], rtol=1e-5)
         assert frac == 1.0, (k, frac, worst)
+    # sampled directions: bit for bit
+    n = len(pos)
+    u3 = U[:n, 5:8].contiguous()
+    assert np.array_equal(E.sample_diffuse(u3[:, 1:3], nrm)[0].numpy(), g["dir_diffuse"])
+    assert np.array_equal(E.sample_specular(u3[:, 1:3], -d, nrm, levels[2])[0].numpy(), g["dir_specular"])
+    with torch.no_grad():
+        wi, pdf, w = E.sample_brdf(u3[:, 0], u3[:, 1:3], -d, nrm, mat_fn(pos))
+    assert np.array_equal(wi.numpy(), g["dir_brdf"])
+    assert relclose(pdf.numpy(), g["dir_brdf_pdf"], rtol=1e-5)[0] == 1.0 and relclose(w.numpy(), g["dir_brdf_w"], rtol=1e-5)[0] == 1.0
+    # the reference on torch's libm: estimators that never evaluate the field at a secondary hit are unaffected ...
+    for k in ["L", "bake_diff"] + ["bake_spec%d_%d" % (j, i) for j in (0, 1) for i in range(6)]:
+        frac, worst = relclose(checks[k].numpy(), g_libm[k], rtol=1e-4)
+        assert frac == 1.0, (k, frac, worst)
+    # ... the others differ from it exactly as much as the reference differs from itself across libms (measured: L_full 95.3 %,
+    # det_diff 88.9 %, det_spec 93-99.6 % of pixels within 1e-3; everything within 5e-2)
+    for k in ("L_full", "det_diff", "det_spec0_0", "det_spec0_2", "det_spec0_5"):
+        frac, worst = relclose(checks[k].numpy(), g_libm[k], rtol=1e-3)
+        assert frac >= 0.85 and worst < 6e-2, (k, frac, worst)
+        assert relclose(g[k], g_libm[k], rtol=1e-3)[0] < 1.0        # the two reference runs really differ
+
+
+def test_shared_trig_accuracy():
+    """oracle/trig.c (== iris_b200/csrc/trig.cuh) against libm in double precision on the ranges the samplers use."""
+    from oracle import trig as T
+    rng = np.random.default_rng(0)
+
+    def ulps(got, ref64):
+        return np.abs(got.astype(np.float64) - ref64) / np.maximum(np.spacing(np.abs(ref64.astype(np.float32))).astype(np.float64), 1e-45)
+    x = (rng.random(400_000) * 2 * np.pi).astype(np.float32)
+    s, c = T.sincos(torch.from_numpy(x))
+    assert np.abs(s.numpy() - np.sin(x.astype(np.float64))).max() < 1.2e-7 and np.abs(c.numpy() - np.cos(x.astype(np.float64))).max() < 1.2e-7
+    x = (rng.random(400_000) * np.pi / 2).astype(np.float32)
+    s, c = T.sincos(torch.from_numpy(x))
+    assert ulps(s.numpy(), np.sin(x.astype(np.float64))).max() < 1.6 and ulps(c.numpy(), np.cos(x.astype(np.float64))).max() < 1.6
+    u = rng.random(400_000).astype(np.float32)
+    assert ulps(T.asin(torch.from_numpy(u)).numpy(), np.arcsin(u.astype(np.float64))).max() < 2.5
+    assert ulps(T.acos(torch.from_numpy(u)).numpy(), np.arccos(u.astype(np.float64))).max() < 1.6
+    e = T.acos(torch.tensor([1.0, 0.0, -1.0, 1.0000001]))
+    assert e[0] == 0.0 and abs(float(e[1]) - np.pi / 2) < 1e-7 and abs(float(e[2]) - np.pi) < 3e-7 and torch.isnan(e[3])
+    e = T.asin(torch.tensor([1.0, 0.0, -1.0, -1.0000001]))
+    assert abs(float(e[0]) - np.pi / 2) < 1e-7 and e[1] == 0.0 and abs(float(e[2]) + np.pi / 2) < 1e-7 and torch.isnan(e[3])
 
 
 @pytest.mark.parametrize("name", ["small", "c1"])
 def test_single_forward_backward_golden(name, relclose):
-    g = np.load(os.path.join(GOLD, name + ".npz"))
+    """path_tracing_single forward + gradients against the reference's own run with the shared trig definitions (`*_st.npz`, every
+    pixel to 1e-5); against the run on torch's libm (`*.npz`) one C1 pixel of 4096 takes a different BSDF path (stated delta)."""
+    g = np.load(os.path.join(GOLD, name + "_st.npz"))
+    g_libm = np.load(os.path.join(GOLD, name + ".npz"))
     c, osc, em, p, mat_fn, r, U = _setup(name, learn=True)
     L = E.path_tracing_single(osc, em, mat_fn, r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], c["spp"], U[:, :8])
     frac, worst = relclose(L.detach().numpy(), g["L"], rtol=1e-5)
     assert frac == 1.0, (frac, worst)
+    frac, worst = relclose(L.detach().numpy(), g_libm["L"], rtol=1e-5)
+    assert frac >= 0.9995, (frac, worst)
     (L * torch.as_tensor(c["Gw"])).sum().backward()
     K = c["sc"].n_emitters
     # emitter radiance: only rows [0,K) receive gradient (SURVEY 8a-a9 quirk)

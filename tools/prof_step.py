@@ -1,11 +1,12 @@
 """One path_tracing_single forward + adjoint (field + emitter gradients) at 1280x960, spp 8, for ncu captures: the first
 k_trace_queue launch traces one full 2^23-sample chunk (16.8 M rays), the launch size bench.py times."""
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
 from iris_b200 import core, scenes
 dev = torch.device("cuda", 0)
-sc = scenes.room(1_000_000, 16, seed=0)
+sc = scenes.room(int(os.environ.get("IRIS_PROF_TRIS", "1000000")), 16, seed=0)
 scene = core.Scene(sc.vertices, sc.faces, 0)
 params = torch.empty(9216 + 27954112).uniform_(-1e-4, 1e-4)
 params[:9216].uniform_(-0.2, 0.2)
