@@ -9,6 +9,9 @@ written against `iris_slf_*` (include/iris_b200.h).
     for view in views:  baker.scatter_add(positions, radiance, valid)     # pass 3   :118-135
     vslf = baker.finalize()                                               #          :138-145  -> dict in the reference's vslf.npz layout
 
+`SLFBaker.from_vslf(state_dict)` is the entry of slf_refine.py:85-108: the occupancy mask and bounds of an existing vslf.npz are kept,
+the radiance is re-accumulated from scratch (there with the trained CRF's `inverse`, iris_b200.crf.EmorCRF.inverse) and averaged.
+
 `finalize()` returns {'mask', 'voxel_min', 'voxel_max', 'weight': {'inds', 'radiance', 'count'}} -- what `torch.save(..., 'vslf.npz')`
 writes in the reference and what SLFEmitter / iris_b200.core.ShadingTables.set_slf load; `device_tables()` hands the int32 index
 grid and the radiance table to the estimators without the round trip through int64.
@@ -36,6 +39,22 @@ class SLFBaker:
         self.n_cells = 0
         self.sum = self.count = None
 
+    @classmethod
+    def from_vslf(cls, state_dict, device="cuda:0"):
+        """slf_refine.py:85-87: VoxelSLF(state_dict['mask'], state_dict['voxel_min'], state_dict['voxel_max']) -- same voxels, same
+        index grid (rank of the occupied voxels in raster order, model/slf.py:29-32), radiance and count back to zero.  state_dict is the
+        dict `torch.load('vslf.npz')` returns (or finalize()'s)."""
+        mask = state_dict["mask"]
+        mask = mask if torch.is_tensor(mask) else torch.as_tensor(mask)
+        b = cls(int(mask.shape[0]), device)
+        if tuple(mask.shape) != (b.H, b.H, b.H):
+            raise ValueError("vslf mask must be (H,H,H)")
+        b.set_bounds(state_dict["voxel_min"], state_dict["voxel_max"])
+        b.occupancy = mask.reshape(-1).to(device=b.device, dtype=torch.int32).contiguous()
+        b._first = False
+        b.build_index()
+        return b
+
     @staticmethod
     def _prep(positions, valid):
         positions = positions.reshape(-1, 3).float().contiguous()
@@ -58,8 +77,11 @@ class SLFBaker:
         self.voxel_min, self.voxel_max = float(voxel_min), float(voxel_max)
 
     def set_bounds_from_observed(self, dataset="synthetic"):
-        """slf_bake.py:87-93, in fp32 like the reference's 0-dim tensors."""
+        """slf_bake.py:87-93, in fp32 like the reference's 0-dim tensors.  The reference's running min / max start from 1000. and 0.0
+        (:73-74), i.e. the bounds are min(1000, min p) and max(0, max p): kept, so that a scene on one side of the origin gets the same
+        grid."""
         lo, hi = (torch.tensor(v, dtype=torch.float32) for v in self.observed_bounds())
+        lo, hi = torch.minimum(lo, torch.tensor(1000.0)), torch.maximum(hi, torch.tensor(0.0))
         if dataset in ("synthetic", "real"):
             lo, hi = 1.1 * lo, 1.1 * hi
         else:

@@ -1,7 +1,8 @@
 """oracle/emitter_extract.py -- TEST INFRASTRUCTURE.  torch (CPU) restatement of the reference's emitter extraction,
-extract_emitter_ldr.py:76-110.  The reference reduces with torch_scatter.scatter(..., reduce='sum') (third-party, absent here:
-parity with it is unpinned); a scatter-sum over an index is restated with index_add_, everything else is the reference's own
-torch expression order."""
+extract_emitter_ldr.py:76-110.  The reference reduces with torch_scatter.scatter(..., reduce='sum') (third-party, absent here); a
+scatter-sum over an index is restated with index_add_, everything else is the reference's own torch expression order.
+Pinned by tests/golden/emitter_extract.npz: the output of the reference's own script executed unmodified through
+oracle/refharness.run_extract_emitter_script (torch_scatter stubbed by its documented scatter-sum semantics)."""
 import torch
 import torch.nn.functional as NF
 

@@ -78,6 +78,102 @@ def load_reference():
     return _MODS
 
 
+def load_reference_crf():
+    """Import the reference's crf/model_crf.py (EmorCRF on the real EMoR tables crf/emor.txt) with its absent third-party imports
+    stubbed: torch_interpolations -> oracle/crf.RegularGridInterpolator (the package's published 1-D algorithm), matplotlib -> empty."""
+    if "crf" in _MODS:
+        return _MODS["crf"]
+    from . import crf as ocrf
+    sys.dont_write_bytecode = True
+    ti = types.ModuleType("torch_interpolations")
+    ti.RegularGridInterpolator = ocrf.RegularGridInterpolator
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    saved = {k: sys.modules.get(k) for k in ("torch_interpolations", "matplotlib", "matplotlib.pyplot", "crf", "const")}
+    sys.modules.update({"torch_interpolations": ti, "matplotlib": mpl, "matplotlib.pyplot": mpl.pyplot})
+    for k in ("crf", "const"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    try:
+        os.chdir(REF)                                     # crf/emor.py:14-17 resolves emor.txt from the working directory
+        import crf.model_crf as mc
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    for k in list(sys.modules):
+        if k == "crf" or k.startswith("crf.") or k == "const":
+            if getattr(sys.modules[k], "__file__", "").startswith(REF):
+                _MODS["_" + k] = sys.modules.pop(k)
+    for k, v in saved.items():
+        if v is not None:
+            sys.modules[k] = v
+        elif k in ("torch_interpolations", "matplotlib", "matplotlib.pyplot"):
+            sys.modules.pop(k, None)
+    _MODS["crf"] = mc
+    return mc
+
+
+def run_extract_emitter_script(scene, views, threshold):
+    """Execute the reference's extract_emitter_ldr.py (its `main()`, mode 'export', lines 72-115) UNMODIFIED on CPU and return the
+    emitter.pth dict it writes.  The script's absent imports are stubbed for the duration of the run: mitsuba (load_dict -> the CPU
+    closest-hit scene), utils.dataset (a list of {'rays','rgbs'} batches = `views`), utils.path_tracing.ray_intersect (oracle/intersect.c),
+    trimesh.load_mesh (the scene's own arrays), torch_scatter.scatter(src, index, 0, out, reduce='sum') -> out.index_add (the
+    package's documented semantics), and torch.device(0) -> cpu."""
+    import runpy
+    from .intersect import OracleScene
+    osc = OracleScene(scene.vertices, scene.faces)
+    sys.dont_write_bytecode = True
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    class _Dataset(list):
+        img_hw = (0, 0)
+
+    def make_dataset(*a, **k):
+        return _Dataset([{"rays": torch.as_tensor(r), "rgbs": torch.as_tensor(c)} for r, c in views])
+
+    def scatter(src, index, dim, out, reduce="sum"):
+        assert dim == 0 and reduce == "sum"
+        return out.index_add(0, index, src)
+
+    stubs = {
+        "mitsuba": mod("mitsuba", set_variant=lambda *a, **k: None, load_dict=lambda d: osc),
+        "utils": mod("utils", __path__=[]),
+        "utils.dataset": mod("utils.dataset", __path__=[], InvRealDatasetLDR=make_dataset, InvSyntheticDatasetLDR=make_dataset),
+        "utils.dataset.scannetpp": mod("utils.dataset.scannetpp", __path__=[]),
+        "utils.dataset.scannetpp.dataset": mod("utils.dataset.scannetpp.dataset", InvScannetpp=make_dataset),
+        "utils.path_tracing": mod("utils.path_tracing", ray_intersect=lambda sc, xs, ds: sc.ray_intersect(xs, ds)),
+        "trimesh": mod("trimesh", load_mesh=lambda p: types.SimpleNamespace(vertices=np.asarray(scene.vertices), faces=np.asarray(scene.faces).astype(np.int64))),
+        "torch_scatter": mod("torch_scatter", scatter=scatter),
+    }
+    saved = {k: sys.modules.get(k) for k in list(stubs) + ["const"]}
+    argv, real_device = sys.argv, torch.device
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "scene.obj"), "w").write("# geometry comes from the trimesh stub\n")
+        try:
+            sys.modules.update(stubs)
+            sys.modules.pop("const", None)
+            sys.path.insert(0, REF)
+            sys.argv = ["extract_emitter_ldr.py", "--scene", td, "--output", td, "--dataset", "synthetic", "--threshold", repr(float(threshold))]
+            torch.device = lambda *a, **k: real_device("cpu")
+            runpy.run_path(os.path.join(REF, "extract_emitter_ldr.py"), run_name="__main__")
+        finally:
+            torch.device = real_device
+            sys.argv = argv
+            sys.path.remove(REF)
+            _MODS["_const_extract"] = sys.modules.pop("const", None)
+            for k, v in saved.items():
+                if v is not None:
+                    sys.modules[k] = v
+                else:
+                    sys.modules.pop(k, None)
+        return torch.load(os.path.join(td, "emitter.pth"))
+
+
 def make_emitter(scene, H, learn=True):
     """Write the scene's emitter.pth / vslf.npz to a temp dir in the reference's on-disk format
     (extract_emitter_ldr.py:109-115, slf_bake.py:140-145) and load them with the reference classes."""

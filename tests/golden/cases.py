@@ -87,3 +87,48 @@ def slf_inputs(n_views=3, n=30000, seed=33):
         views.append((pos, valid))
         rads.append(torch.rand(n, 3, generator=g) * 4.0)
     return views, rads
+
+
+def crf_inputs(n=6000, seed=41):
+    """Seeded inputs of the EmorCRF case: HDR values that under- and overshoot [0,1] after exposure, per-row exposures, bin-edge
+    values, a weight set of realistic size, LDR values for the inverse."""
+    g = torch.Generator().manual_seed(seed)
+    hdr = torch.rand(n, 3, generator=g) * 1.6 - 0.2
+    hdr[:1024, 0] = torch.linspace(0, 1, 1024)                 # exactly on the knots (exposure 1 below)
+    hdr[0, 1], hdr[1, 1], hdr[2, 1] = 0.0, 1.0, 1.0 - 2.0 ** -24
+    exposure = torch.rand(n, 1, generator=g) * 1.5 + 0.25
+    exposure[:1024] = 1.0
+    weight = (torch.rand(3, 11, generator=g) - 0.5) * 0.2
+    d_ldr = torch.randn(n, 3, generator=g)
+    ldr = torch.rand(n, 3, generator=g) * 1.2 - 0.1
+    ldr[:1024, 2] = torch.linspace(0, 1, 1024)
+    return dict(hdr=hdr, exposure=exposure, weight=weight, d_ldr=d_ldr, ldr=ldr)
+
+
+def emitter_extract_inputs(n_views=3, side=40, seed=51):
+    """Seeded inputs of the emitter-extraction case (extract_emitter_ldr.py:76-110): camera rays of a few views of the Cornell room and
+    LDR colours that saturate on the light, on every 53rd triangle, and NOT QUITE (mean just under the threshold) on every 59th."""
+    from oracle.intersect import OracleScene
+    sc = scenes.cornell(seed=0)
+    osc = OracleScene(sc.vertices, sc.faces)
+    g = torch.Generator().manual_seed(seed)
+    views = []
+    for v in range(n_views):
+        rays = sc.camera_rays(side, side, view=v)
+        prim = osc.intersect_raw(rays[:, 0:3], rays[:, 3:6])["prim"].astype(np.int64)
+        rgb = torch.rand(len(rays), 3, generator=g) * 0.9
+        hit = prim >= 0
+        lit = hit & (sc.is_emitter[np.maximum(prim, 0)] | (prim % 53 == 0))
+        rgb[torch.as_tensor(lit)] = torch.tensor([0.97, 1.0, 0.95])
+        almost = torch.as_tensor(hit & (prim % 59 == 0) & ~lit)
+        rgb[almost] = torch.tensor([0.9, 0.985, 0.7])
+        views.append((rays, rgb.numpy()))
+    return sc, views
+
+
+def slf_refine_inputs(views, seed=37):
+    """Seeded LDR colours + exposures for the refine pass (slf_refine.py:88-104) over the points of slf_inputs()."""
+    g = torch.Generator().manual_seed(seed)
+    ldr = [torch.rand(len(p), 3, generator=g) for p, _ in views]
+    exposure = [float(torch.rand(1, generator=g)) + 0.5 for _ in views]
+    return ldr, exposure

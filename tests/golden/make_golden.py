@@ -81,6 +81,23 @@ def slf_golden():
     assert torch.equal(out["weight"]["radiance"], own["weight"]["radiance"]) and torch.equal(out["mask"], own["mask"])
     g = dict(voxel_min=np.float64(out["voxel_min"]), voxel_max=np.float64(out["voxel_max"]), mask=np.packbits(out["mask"].numpy().reshape(-1)),
              inds=out["weight"]["inds"].numpy().astype(np.int32), radiance=out["weight"]["radiance"].numpy(), count=out["weight"]["count"].numpy().astype(np.int32))
+    # the refine pass, slf_refine.py:85-108: the reference's VoxelSLF rebuilt from the saved mask / bounds, radiance re-accumulated from
+    # LDR colours through the reference's EmorCRF.inverse (real EMoR tables, the weights of the CRF case), mean pooling
+    mc = RH.load_reference_crf()
+    crf = mc.EmorCRF(dim=11)
+    with torch.no_grad():
+        crf.weight.copy_(cases.crf_inputs()["weight"])
+    ldr, exposure = cases.slf_refine_inputs(views)
+    ref2 = ref_slf(out["mask"], out["voxel_min"], out["voxel_max"])
+    with torch.no_grad():
+        for (pos, valid), c, e in zip(views, ldr, exposure):
+            rad = crf.inverse(c, e)
+            if not valid.any():
+                continue
+            ref2.scatter_add(pos[valid], rad[valid])
+        ref2.radiance = ref2.radiance / ref2.count[..., None].float().clamp_min(1)
+    assert torch.equal(ref2.inds, out["weight"]["inds"])
+    g["refine_radiance"], g["refine_count"] = ref2.radiance.numpy(), ref2.count.numpy().astype(np.int32)
     np.savez_compressed(os.path.join(HERE, "slf.npz"), **g)
     print("slf.npz", {k: getattr(v, "shape", v) for k, v in g.items()}, "cells", len(g["count"]))
 
@@ -130,7 +147,55 @@ def small_case(shared_trig):
     return g
 
 
+def crf_golden():
+    """tests/golden/crf.npz: the reference's own EmorCRF (crf/model_crf.py, imported from /root/reference with the absent
+    torch_interpolations stubbed by its published 1-D algorithm) on the REAL EMoR tables (crf/emor.txt): forward + autograd
+    gradients, the inverse table, inverse(), and the weight fit.  f0 and the 11 basis curves are stored with the outputs (12 x 1024
+    floats of the public EMoR database) because /root/reference does not exist where the GPU tests run."""
+    mc = RH.load_reference_crf()
+    x = cases.crf_inputs()
+    m = mc.EmorCRF(dim=11)
+    with torch.no_grad():
+        m.weight.copy_(x["weight"])
+    hdr = x["hdr"].clone().requires_grad_(True)
+    ldr = m(hdr, x["exposure"])
+    (ldr * x["d_ldr"]).sum().backward()
+    g = dict(f0=m.f0.numpy()[0], basis=m.basis.numpy(), ldr=ldr.detach().numpy(), d_hdr=hdr.grad.numpy(), d_weight=m.weight.grad.numpy(),
+             crf=m.get_crf().detach().numpy(), inv_crf=m.get_inv_crf().detach().numpy(),
+             hdr_inv=m.inverse(x["ldr"], x["exposure"]).detach().numpy(),
+             ldr_scalar_exposure=m(x["hdr"], torch.tensor(0.7)).detach().numpy())
+    # a monotone weight set (gamma-like camera): forward -> inverse is a round trip; and the weight fit of that response
+    m2 = mc.EmorCRF(dim=11)
+    target = torch.linspace(0, 1, 1024).pow(1 / 2.2)[None].expand(3, 1024).numpy() * np.array([[1.0], [0.97], [1.02]], np.float32)
+    g["fit_target"] = target.astype(np.float32)
+    g["fit_weight"] = m2.cal_weight_fitting_crf(target).astype(np.float32)
+    m2.initialize_weight(target)
+    g["fit_crf"] = m2.get_crf().detach().numpy()
+    g["fit_inv_crf"] = m2.get_inv_crf().detach().numpy()
+    g["fit_roundtrip"] = m2.inverse(m2(x["hdr"], x["exposure"]).detach(), x["exposure"]).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "crf.npz"), **g)
+    print("crf.npz", {k: v.shape for k, v in g.items()})
+
+
+def emitter_extract_golden():
+    """tests/golden/emitter_extract.npz: the reference's own extract_emitter_ldr.py (mode 'export') executed unmodified through the
+    harness on the seeded views of cases.emitter_extract_inputs()."""
+    sc, views = cases.emitter_extract_inputs()
+    out = RH.run_extract_emitter_script(sc, views, 0.99)
+    g = {k: np.asarray(v.numpy()) for k, v in out.items()}
+    g["is_emitter"] = np.packbits(g["is_emitter"])
+    g["emitter_radiance_shape"] = np.array(out["emitter_radiance"].shape)
+    g["emitter_radiance_absmax"] = np.float32(out["emitter_radiance"].abs().max().item())
+    del g["emitter_radiance"]
+    np.savez_compressed(os.path.join(HERE, "emitter_extract.npz"), **g)
+    print("emitter_extract.npz", {k: v.shape for k, v in g.items()}, "K =", int(out["is_emitter"].sum()))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "emitter_extract":
+        return emitter_extract_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "crf":
+        return crf_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "shading":
         return shading_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "slf":
@@ -160,6 +225,8 @@ def main():
         return
     shading_golden()
     slf_golden()
+    crf_golden()
+    emitter_extract_golden()
 
 
 if __name__ == "__main__":

@@ -244,3 +244,46 @@ def test_emitter_extract_oracle_basic():
     out = OE.extract(views, V, F, 0.9)
     assert out["is_emitter"].tolist() == [True, False] and out["triangle_count"].tolist() == [2.0, 1.0]
     assert torch.allclose(out["emitter_area"], torch.tensor([2.0])) and torch.allclose(out["emitter_normal"], torch.tensor([[0., 0., 1.]]))
+
+
+def test_crf_oracle_matches_reference_golden():
+    """oracle/crf.py against tests/golden/crf.npz (the reference's own EmorCRF on the real EMoR tables): forward + autograd gradients,
+    the inverse table, inverse(), the weight fit.  The mirror's torch-only methods (get_inv_crf, cal_weight_fitting_crf) are checked too."""
+    from oracle import crf as OC
+    g = np.load(os.path.join(GOLD, "crf.npz"))
+    x = cases.crf_inputs()
+    f0, basis = torch.as_tensor(g["f0"])[None], torch.as_tensor(g["basis"])
+    hdr = x["hdr"].clone().requires_grad_(True)
+    w = x["weight"].clone().requires_grad_(True)
+    ldr = OC.emor_forward(hdr, x["exposure"], f0, basis, w)
+    (ldr * x["d_ldr"]).sum().backward()
+    assert np.allclose(ldr.detach().numpy(), g["ldr"], rtol=1e-5, atol=2e-6)
+    bad = ~np.isclose(hdr.grad.numpy(), g["d_hdr"], rtol=2e-3, atol=1e-4)
+    assert bad[1024:].mean() < 1e-3                                # rows 0..1023 sit exactly on knots, where the slope is two-valued
+    assert np.allclose(w.grad.numpy(), g["d_weight"], rtol=1e-3, atol=1e-4)
+    assert np.array_equal(OC.inv_crf(f0, basis, x["weight"]).numpy(), g["inv_crf"])
+    assert np.allclose(OC.emor_inverse(x["ldr"], x["exposure"], f0, basis, x["weight"]).numpy(), g["hdr_inv"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(OC.fit_weight(g["fit_target"], g["f0"][None], g["basis"]), g["fit_weight"], rtol=1e-3, atol=1e-4)
+    from iris_b200.crf import EmorCRF
+    m = EmorCRF(dim=11, tables=(g["f0"], g["basis"]))
+    with torch.no_grad():
+        m.weight.copy_(x["weight"])
+    assert np.allclose(m.get_inv_crf().numpy(), g["inv_crf"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(m.cal_weight_fitting_crf(g["fit_target"]), g["fit_weight"], rtol=1e-3, atol=1e-4)
+
+
+def test_emitter_extract_oracle_matches_reference_golden():
+    """oracle/emitter_extract.py against tests/golden/emitter_extract.npz (the reference's own extract_emitter_ldr.py run unmodified)."""
+    from oracle import emitter_extract as OE
+    g = np.load(os.path.join(GOLD, "emitter_extract.npz"))
+    sc, views = cases.emitter_extract_inputs()
+    osc = OracleScene(sc.vertices, sc.faces)
+    vv = []
+    for rays, rgb in views:
+        prim = torch.as_tensor(osc.intersect_raw(rays[:, 0:3], rays[:, 3:6])["prim"].astype(np.int64))
+        vv.append((prim, prim >= 0, torch.as_tensor(rgb)))
+    out = OE.extract(vv, torch.as_tensor(sc.vertices), torch.as_tensor(sc.faces).long(), 0.99)
+    assert np.array_equal(np.packbits(out["is_emitter"].numpy()), g["is_emitter"])
+    assert np.array_equal(out["emitter_vertices"].numpy(), g["emitter_vertices"]) and np.array_equal(out["emitter_area"].numpy(), g["emitter_area"])
+    assert np.array_equal(out["emitter_normal"].numpy(), g["emitter_normal"])
+    assert tuple(out["emitter_radiance"].shape) == tuple(g["emitter_radiance_shape"])
