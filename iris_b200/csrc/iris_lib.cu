@@ -609,6 +609,7 @@ int iris_field_backward(const IrisShadeParams *P, const float *position, const f
     if (n == 0) return IRIS_OK;
     if (!position || !d_mat || !d_params || !workspace) return fail(IRIS_ERR_INVALID, "NULL array");
     if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(IRIS_ERR_INVALID, "workspace must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_params) & 15) return fail(IRIS_ERR_INVALID, "d_params must be 16-byte aligned (16-byte vector reductions into the grid gradient)");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     int rc = ensure_device_setup(dev);
@@ -706,6 +707,7 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
     const int64_t n = n_pixels * spp;
     float *d_mat = nullptr;
     if (d_params) {
+        if (reinterpret_cast<uintptr_t>(d_params) & 15) return fail(IRIS_ERR_INVALID, "d_params must be 16-byte aligned (16-byte vector reductions into the grid gradient)");
         if (!encoded) return fail(IRIS_ERR_INVALID, "the field gradient needs the `encoded` array the forward was given (a record made without it holds no BRDF Jacobians)");
         if (!P->grid_f16 || !P->mlp_f16) return fail(IRIS_ERR_INVALID, "BRDF field tables missing");
         if (!workspace || workspace_bytes < iris_single_workspace_bytes(n_pixels, spp)) return fail(IRIS_ERR_WORKSPACE, "workspace too small");

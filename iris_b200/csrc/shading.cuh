@@ -45,11 +45,16 @@ __device__ __forceinline__ float4 sample4(const IrisSampler &s, int64_t lane, in
 // Everything between the uniforms and a sampled direction is one IEEE rounding per operation, in the order of the reference's
 // ATen chain (products rounded before they are summed; the 1x3 @ 3x3 frame change accumulates left to right), with the
 // transcendentals of trig.cuh: the CPU checker restates the same sequence, so secondary rays agree bit for bit.
+// torch.cross evaluates a1*b2 - a2*b1 inside ONE kernel, where the compiler contracts it to fma(a1, b2, -round(a2*b1)) -- on the CPU
+// build (checked bit for bit) and, by nvcc's own contraction rule, on the CUDA build the reference runs on.  Spelled out here.
+__device__ __forceinline__ f3 cross_torch(f3 a, f3 b) {
+    return mk3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
 // utils/ops.py:12-30
 __device__ __forceinline__ void normal_space(f3 n, f3 &t, f3 &b) {
     const f3 a = fabsf(n.x) <= 0.1f ? mk3(1.f, 0.f, 0.f) : mk3(0.f, 1.f, 0.f);
-    t = normalize_nf(xcross(a, n));
-    b = xcross(n, t);
+    t = normalize_nf(cross_torch(a, n));
+    b = cross_torch(n, t);
 }
 // utils/ops.py:32-44 followed by the frame change of model/brdf.py:32-33
 __device__ __noinline__ f3 sphere_to_world(float theta, float phi, f3 n) {

@@ -83,6 +83,12 @@ static inline float acos_f32(float x) {
     return PIO2_F - fmaf(x * z, asin_poly(z), x);
 }
 
+/* IEEE (correctly rounded) square root.  torch's CPU sqrt kernel is NOT correctly rounded (AVX-512 build of torch 2.11: 0.6 % of
+ * fp32 inputs come back one ulp off; measured against sqrt in double precision), CUDA's sqrtf / torch.sqrt on a GPU and C's
+ * sqrtf are.  The samplers take sqrt(u) before asin / acos and for the emitter barycentrics, so the checker uses this one. */
+void oracle_sqrt(const float *x, int64_t n, float *y) {
+    for (int64_t i = 0; i < n; ++i) y[i] = sqrtf(x[i]);
+}
 void oracle_sincos(const float *x, int64_t n, float *s, float *c) {
     for (int64_t i = 0; i < n; ++i) sincos_f32(x[i], s + i, c + i);
 }

@@ -6,7 +6,8 @@ bit-identical directions (reference call sites: model/brdf.py:28-29,50-51, utils
 flows through the samplers in the reference (uniforms and detached roughness in, directions out), so plain
 tensor-in / tensor-out functions are enough.
 
-`patched_torch()` swaps torch.sin / cos / asin / acos for these during a run of the REFERENCE's own code
+`patched_torch()` swaps torch.sin / cos / asin / acos (and sqrt, which torch's CPU build does not round correctly) for these during a
+run of the REFERENCE's own code
 (oracle/refharness.py) -- "the reference with this libm" -- which is how the `*_st` golden vectors are made.
 """
 from __future__ import annotations
@@ -29,6 +30,7 @@ def _lib():
         L.oracle_sincos.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_asin.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         L.oracle_acos.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.oracle_sqrt.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         _READY = True
     return L
 
@@ -67,12 +69,18 @@ def acos(x):
     return _unary("oracle_acos", x)
 
 
+def sqrt(x):
+    """IEEE square root (torch's CPU kernel is one ulp off on 0.6 % of fp32 inputs; CUDA's and C's are exact)."""
+    return _unary("oracle_sqrt", x)
+
+
 @contextlib.contextmanager
 def patched_torch():
     """torch.sin / cos / asin / acos -> the shared definitions, for fp32 CPU tensors without grad (everything
     else falls through to torch's own)."""
-    orig = {k: getattr(torch, k) for k in ("sin", "cos", "asin", "acos")}
-    mine = {"sin": sin, "cos": cos, "asin": asin, "acos": acos}
+    orig = {k: getattr(torch, k) for k in ("sin", "cos", "asin", "acos", "sqrt")}
+    mine = {"sin": sin, "cos": cos, "asin": asin, "acos": acos, "sqrt": sqrt}
+    base_sqrt = torch.Tensor.sqrt
 
     def wrap(k):
         def f(x, *a, **kw):
@@ -82,8 +90,15 @@ def patched_torch():
         return f
     for k in orig:
         setattr(torch, k, wrap(k))
+
+    def tensor_sqrt(self):
+        if self.dtype == torch.float32 and not self.requires_grad and self.device.type == "cpu":
+            return sqrt(self)
+        return base_sqrt(self)
+    torch.Tensor.sqrt = tensor_sqrt                       # the reference writes x.sqrt() (model/brdf.py:28,50, model/emitter.py:241)
     try:
         yield
     finally:
         for k, v in orig.items():
             setattr(torch, k, v)
+        torch.Tensor.sqrt = base_sqrt

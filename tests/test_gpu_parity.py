@@ -996,6 +996,14 @@ def test_c_abi_error_convention(small):
     assert lib.iris_brdf_shading_forward(C.ptr(L), C.ptr(L), C.ptr(L), C.ptr(L), 1, 8, C.ptr(L), None) == -1          # n_levels < 2
     assert lib.iris_slf_mark(C.ptr(o), None, 4, 0.0, 0.0, 32, C.ptr(out), None) == -1                                   # empty voxel range
     assert lib.iris_set_option(b"no_such_option", 1) != 0
+    # a gradient buffer that is not 16-byte aligned (a sliced view of a flat buffer) is refused, not faulted on
+    flat = torch.zeros(9216 + 27954112 + 8, device=dev)
+    x = torch.zeros(4, 3, device=dev)
+    ws2 = torch.zeros(max(lib.iris_field_backward_workspace_bytes(4), 16), dtype=torch.uint8, device=dev)
+    rc = lib.iris_field_backward(ctypes.byref(P), C.ptr(x), C.ptr(torch.zeros(4, 5, device=dev)), 4, ctypes.c_void_p(flat.data_ptr() + 4), None, C.ptr(ws2), ws2.numel(), None)
+    assert rc == -1 and b"aligned" in lib.iris_last_error()
+    assert lib.iris_bsdf_sample(3, C.ptr(x), 3, C.ptr(x), C.ptr(x), None, 0.5, 4, C.ptr(x), None, None, None, None) == -1   # bad mode
+    assert lib.iris_abi_info(0) == C.ABI_VERSION and lib.iris_abi_info(99) == -1
     assert lib.iris_launch_count() == l0
     with pytest.raises(RuntimeError, match="scene is NULL"):                                                               # the Python layer raises
         C.check(lib.iris_intersect(None, C.ptr(o), C.ptr(o), 4, C.ptr(out), None, None, None, None, None))
