@@ -28,23 +28,57 @@ def shard_rows(t, rank=None, world_size=None):
     return t[lo:hi]
 
 
-def allreduce_gradients(tensors, average=False):
-    """Sum (or average) the given gradient tensors over all ranks with a single collective on one flat buffer; in place.
-    Tensors that are None are skipped; returns the number of elements communicated."""
+def interleaved_rows(n_items, block=256, rank=None, world_size=None):
+    """Index tensor of the rows rank `rank` owns when blocks of `block` consecutive rows (pixels of one image region) are dealt
+    round-robin to the ranks: every rank sees every part of every view, so the ranks' loads are equal whatever a region costs
+    ("interleave tiles across ranks rather than whole views").  All spp samples of a pixel stay on one rank."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    n_items, block = int(n_items), int(block)
+    idx = torch.arange(n_items)
+    if world_size == 1:
+        return idx
+    blk = idx // block
+    return idx[(blk % world_size) == rank]
+
+
+def allreduce_gradients(tensors, average=False, big=1 << 20):
+    """Sum (or average) the given gradient tensors over all ranks, in place.  Contiguous fp32 tensors of at least `big` elements
+    (the 112 MB field gradient) are reduced where they lie, each by its own collective; the small ones (emitter rows, CRF weights)
+    travel together in one flat buffer.  All collectives are issued asynchronously and waited for at the end, so the small reduction
+    and the copies around it overlap the big one.  None entries are skipped; returns the number of elements communicated."""
     ts = [t for t in tensors if t is not None]
     rank, ws = world()
     if ws == 1 or not ts:
         return 0
-    flat = torch.cat([t.reshape(-1).float() for t in ts])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    in_place = [t for t in ts if t.numel() >= big and t.is_contiguous() and t.dtype == torch.float32]
+    small = [t for t in ts if not any(t is b for b in in_place)]
+    work = [dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True) for t in in_place]
+    flat = None
+    if small:
+        flat = torch.cat([t.reshape(-1).float() for t in small])
+        work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+    for w in work:
+        w.wait()
     if average:
-        flat /= ws
-    o = 0
-    for t in ts:
-        n = t.numel()
-        t.copy_(flat[o:o + n].view_as(t))
-        o += n
-    return int(flat.numel())
+        for t in in_place:
+            t /= ws
+    if flat is not None:
+        if average:
+            flat /= ws
+        o = 0
+        for t in small:
+            n = t.numel()
+            t.copy_(flat[o:o + n].view_as(t))
+            o += n
+    return int(sum(t.numel() for t in ts))
+
+
+def rank_seed(seed):
+    """Decorrelate the Philox streams of data-parallel ranks that were seeded alike (const.set_random_seed seeds every process with
+    the same value): rank r uses seed + r * golden-ratio constant (mod 2^64); rank 0 / single process keep the seed."""
+    rank, ws = world()
+    return (int(seed) + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
 
 def gather_rows(local, n_total):

@@ -37,7 +37,8 @@ def next_sampler(device):
     if _INJECT:
         return core.Sampler(U=_INJECT[-1].to(device))
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # advances torch's global generator like torch.rand would
-    return core.Sampler(seed=seed)
+    from . import dist as idist
+    return core.Sampler(seed=idist.rank_seed(seed))              # ranks seeded alike still draw independent sample streams
 
 
 # ------------------------------------------------------------------------------------------------ scene handle

@@ -21,6 +21,18 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_interleaved_rows_partition_and_balance():
+    for n, block, ws in ((1000, 64, 3), (1228800, 256, 8), (5, 256, 2), (0, 16, 4)):
+        parts = [idist.interleaved_rows(n, block, r, ws) for r in range(ws)]
+        allidx = torch.cat(parts).sort().values
+        assert torch.equal(allidx, torch.arange(n))                       # a partition
+        for p in parts:                                                   # whole blocks only: the spp samples of a pixel and its neighbours stay together
+            assert all(int(b) // block == int(a) // block or int(b) % block == 0 for a, b in zip(p[:-1][:2000], p[1:][:2000]))
+        if n >= block * ws * 4:
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= block
+
+
 def _worker(rank, ws, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -36,7 +48,11 @@ def _worker(rank, ws, port, q):
     loss_local, dL = step.mse_and_cotangent(L_local, target[lo:hi])
     d_rad = torch.einsum("pc,pck->k", dL, A[lo:hi]).reshape(K, 3)
     d_crf = torch.full((3, 2), float(rank + 1))
-    n = idist.allreduce_gradients([d_rad, None, d_crf])
+    d_big = torch.full((1 << 12,), float(rank + 1))                      # reduced in place by its own collective (`big` lowered for the test)
+    keep_ptr = d_big.data_ptr()
+    n = idist.allreduce_gradients([d_rad, None, d_crf, d_big], big=1 << 12)
+    assert d_big.data_ptr() == keep_ptr and bool((d_big == 3.0).all())
+    assert idist.rank_seed(5) == (5 + rank * 0x9E3779B97F4A7C15) % 2 ** 64
     loss = loss_local.clone()
     dist.all_reduce(loss)
     L_all = idist.gather_rows(L_local, P)
@@ -65,7 +81,7 @@ def test_two_rank_step_matches_single_process():
     L = A @ radiance.reshape(-1)
     ref = ((L - target) ** 2).mean()
     ref.backward()
-    assert n == K * 3 + 6
+    assert n == K * 3 + 6 + (1 << 12)
     assert abs(loss - ref.item()) < 1e-5 * abs(ref.item())
     assert torch.allclose(d_rad, radiance.grad, rtol=1e-4, atol=1e-6)
     assert torch.equal(d_crf, torch.full((3, 2), 3.0))

@@ -1080,3 +1080,72 @@ def test_full_size_properties_c3_scene():
     tables.t["slf_radiance"] = keep
     tables.set_radiance(r0)
     assert float(Ld.max()) <= 1 + 1e-5 and float(Ld.mean()) > 0.99 and float((Ld.min(dim=-1)[0] > 0.98).float().mean()) > 0.95, (float(Ld.min()), float(Ld.mean()))
+
+
+def _subsample_parity(n_tris, n_px, spp, hit_rays, bake_spp=None):
+    """Shared body of the full-size parity tests: the BASELINE room at n_tris triangles against the ORACLE (C BVH + torch estimators) on a
+    pixel subsample the oracle finishes in seconds.  Hits bit-exact; path_tracing_single radiance, emitter gradient and (bake_spp) the
+    diffuse shading map within 1e-3."""
+    dev = _gpu()
+    from iris_b200 import core, scenes
+    from oracle import estimators as E
+    from oracle import field as OF
+    from oracle.intersect import OracleScene
+    sc = scenes.room(n_tris, 16, seed=0)
+    scene = core.Scene(sc.vertices, sc.faces, 0)
+    osc = OracleScene(sc.vertices, sc.faces)
+    st = scene.stats()
+    assert st["n_tris"] == sc.n_tris and 2 * st["max_depth"] <= 48
+    # ---- closest hits: camera rays of two views, secondary-ray pattern, vertex-aimed and axis-parallel rays
+    o, d = _rays_for_parity(sc, osc, hit_rays // 4, seed=n_tris % 1000)
+    cam = np.concatenate([sc.camera_rays(320, 240, view=v) for v in (1, 2)])
+    o, d = np.concatenate([o, cam[:, 0:3]]), np.concatenate([d, cam[:, 3:6]])
+    ref = _check_intersect(scene, osc, o, d, dev)
+    assert len(o) >= hit_rays and (ref["prim"] >= 0).mean() > 0.9
+    # ---- path_tracing_single on a strided pixel subsample of one full-resolution view, injected samples
+    H = 256
+    params = cases.golden_params()
+    vmin, vmax = sc.voxel_bounds()
+    tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(H), params, (vmin, vmax))
+    em = E.Emitter(sc.emitter_dict(), sc.slf_dict(H), learn=True)
+    rays_all = sc.camera_rays(1280, 960, view=1)
+    r = torch.as_tensor(rays_all[:: max(1, len(rays_all) // n_px)][:n_px].copy())
+    rng = np.random.default_rng(17)
+    U = torch.as_tensor(np.minimum(rng.random((len(r) * spp, 8), dtype=np.float32), np.float32(0.99999)))
+    Gw = torch.as_tensor(rng.standard_normal((len(r), 3)).astype(np.float32))
+    L, rec = core.single_forward(scene, tables, r.to(dev), spp, core.Sampler(U=U.to(dev)), True, want_encoded=False)
+    d_rad = core.single_backward(tables, Gw.to(dev), spp, rec).cpu().numpy()
+    Lo = E.path_tracing_single(osc, em, lambda x: OF.material(x, params, vmin, vmax), r[:, 0:3], r[:, 3:6], r[:, 6:9], r[:, 9:12], spp, U)
+    (Lo * Gw).sum().backward()
+    frac, worst = _frac_close(L.cpu().numpy(), Lo.detach().numpy())
+    assert frac >= 0.995, ("path_tracing_single", n_tris, frac, worst)
+    frac, worst = _frac_close(d_rad, em.radiance.grad[:sc.n_emitters].numpy(), rtol=2e-3)
+    assert frac == 1.0, ("d_radiance", n_tris, worst)
+    if bake_spp:
+        pos, nrm, _, tri, valid = osc.ray_intersect(r[:, 0:3], r[:, 3:6])
+        pos, nrm = pos[valid], nrm[valid]
+        Ub = torch.as_tensor(rng.random((len(pos) * bake_spp, 2), dtype=np.float32))
+        got = core.bake(scene, tables, 0, 1.0, pos.to(dev), nrm.to(dev), None, bake_spp, core.Sampler(U=Ub.to(dev))).cpu().numpy()
+        want = E.bake_diffuse(osc, em, pos, nrm, bake_spp, Ub).detach().numpy()
+        frac, worst = _frac_close(got, want)
+        assert frac >= 0.995, ("bake_diffuse", n_tris, frac, worst)
+        wo = -r[:, 3:6][valid]
+        g0, g1 = core.bake(scene, tables, 1, 0.412, pos.to(dev), nrm.to(dev), wo.to(dev), bake_spp, core.Sampler(U=Ub.to(dev)))
+        w0, w1 = E.bake_specular(osc, em, pos, wo, nrm, 0.412, bake_spp, Ub)
+        for a, b, name in ((g0, w0, "spec0"), (g1, w1, "spec1")):
+            frac, worst = _frac_close(a.cpu().numpy(), b.detach().numpy())
+            assert frac >= 0.99, ("bake_" + name, n_tris, frac, worst)
+
+
+def test_c2_c3_size_parity_against_the_oracle():
+    """BASELINE configs[1]/[2] geometry (1M-triangle room): 260k rays bit-exact; a 4096-pixel subsample of a 1280x960 view at spp 32
+    (the C3 chunk size) through path_tracing_single fwd + emitter adjoint, and the same pixels through the diffuse / specular bake at
+    spp 64 (the C2 setting), against the oracle."""
+    _subsample_parity(1_000_000, 4096, 32, 100_000, bake_spp=64)
+
+
+def test_c5_size_parity_against_the_oracle():
+    """BASELINE configs[4] geometry (5M-triangle room: BVH + triangles no longer fit the 126 MB L2): 350k rays bit-exact vs the oracle
+    (device LBVH on the GPU, binned SAH in the oracle -- two different trees, one answer), and a 2048-pixel subsample at spp 16
+    through path_tracing_single fwd + emitter adjoint."""
+    _subsample_parity(5_000_000, 2048, 16, 200_000)
