@@ -268,7 +268,8 @@ int64_t iris_launch_count(void);
 
 /* Implementation switches (process-wide; every alternative is tested equal to the default).  Defaults first:
  *   "field_forward_impl"      1 tcgen05 + TMEM 128-row tiles | 0 mma.sync warp tiles
- *   "field_backward_impl"     1 dgrad + wgrad fused in one tcgen05 kernel (used when the encoded inputs are available) | 0 mma.sync dgrad + TF32 wgrad kernels
+ *   "field_backward_impl"     2 dgrad + wgrad fused in one tcgen05 kernel, TMA tile loads / stores, 8 epilogue warps (used when the encoded inputs are
+ *                             available) | 1 the first-generation fused kernel (4 warps, per-thread tile copies) | 0 mma.sync dgrad + TF32 wgrad kernels
  *   "single_impl"             1 wavefront bounce (generate -> persistent ray-queue trace -> shade) | 0 one fused kernel
  *   "single_chunk_log2"       23: samples per ray-queue chunk = 2^value (10..30)
  *   "wave_impl"               1 path_tracing / det / indirect bounces through the ray queue | 0 fused bounce kernel

@@ -1,0 +1,317 @@
+// field_bwd_tc5v2.cuh -- second generation of the fused field adjoint (dgrad + wgrad in one tcgen05 kernel, field_bwd_tc5.cuh is
+// the first; same mathematics, same rounding points, same TMEM accumulators for dW1, dW2, dW3^T).  What changed, driven by the ncu
+// capture of the first kernel (profiles/r2a_k_field_backward_tc5.txt: 8 warps per SM, issue slots 23 % busy, tensor pipe 12 %,
+// 6.8 M local-memory instructions per launch -- a latency chain of six serial "sync -> MMA -> wait -> epilogue" rounds per tile):
+//   * TMA: the 16 KB X tile (this tile's 128 rows of the `encoded` array) arrives as eight cp.async.bulk.tensor boxes (8 halfs x 128
+//     rows of a 2-D tensor map over the row-major [n][64] fp16 array), each landing as one 2 KB K-chunk of the canonical K-major
+//     core-matrix layout; out-of-range rows are zero-filled by the hardware; completion is signalled on an mbarrier with expect_tx.
+//     The next tile's X is requested as soon as the last MMA round of the current tile has consumed the buffer, so the load
+//     overlaps the dx^ epilogue.  dx^ leaves the same way: the epilogue writes the tile into shared memory and eight
+//     cp.async.bulk.tensor stores (one bulk group) send it to the [n][64] stream the grid scatter reads.
+//   * 8 epilogue warps per tile instead of 4: TMEM lane quadrant = warp % 4, accumulator columns [32 (warp / 4), +32): one
+//     tcgen05.ld.32x32b.x32 per thread and round, half the per-thread epilogue work, twice the warps to hide its latency.
+//   * packed arithmetic, no local memory.  The ReLU derivative is relu'(acc) of the fp32 accumulator (the checker differentiates
+//     fp16(relu(acc)) straight through the rounding), and a positive accumulator below 2^-25 rounds to an fp16 zero: so h is stored
+//     as max(fp16x2(acc), -0) -- negative pre-activations become MINUS zero, which the tensor core reads as zero -- and the dgrad rounds
+//     recover the mask from the sign bits of the resident h1 / h2 tiles (one 16-byte shared load per 8 columns, PRMT sign replicate,
+//     AND-NOT).  The wgrad operand dh~ = dh^ * (s_i / S) is one HMUL2 by a power of two.
+// Selected by iris_set_option("field_backward_impl", 2) (default); 1 = the first-generation kernel, 0 = the two-kernel mma.sync form.
+#pragma once
+#include <cuda.h>
+
+#include "field_bwd_tc5.cuh"
+
+#define BT6_THREADS 256
+#define BT6_SMEM_BYTES (5 * BT5_TILE_BYTES + 2 * 8192 + 2048 + 16 + 16 + 512 + 32)   // tiles | W1 W2 | W3 | 2 mbarriers | tmem slot | s_i | per-warp maxima
+
+#define TC5_LD32(r, taddr)                                                                                                                    \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22," \
+                 "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"                                                                             \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),    \
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),       \
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),       \
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                                         \
+                 : "r"(taddr))
+
+// fp16x2(max(acc, -0)): relu with the sign of a negative pre-activation kept in the (numerically inert) sign bit of the zero
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("{ .reg .b32 t; cvt.rn.f16x2.f32 t, %1, %2; max.f16x2 %0, t, %3; }" : "=r"(r) : "f"(hi), "f"(lo), "r"(0x80008000u));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// 0xFFFF for every half of h whose sign bit is clear (pre-activation not negative), 0 where it is set
+__device__ __forceinline__ uint32_t relu_mask_f16x2(uint32_t h) {
+    uint32_t neg;
+    asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(neg) : "r"(h));       // selector nibbles 9 / B: replicate the MSB of byte 1 / byte 3
+    return ~neg;
+}
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 b) {
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2 *>(&a), b);
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+// rows [row0, row0 + 128) of a row-major [n][64] fp16 array <-> a K-major tile: box kc = columns [8 kc, 8 kc + 8) = K chunk kc
+__device__ __forceinline__ void tma_load_tile(uint32_t smem_dst, const CUtensorMap *map, int32_t row0, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)BT5_TILE_BYTES) : "memory");
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(smem_dst + kc * TC5_A_LBO), "l"(reinterpret_cast<uint64_t>(map)), "r"(8 * kc), "r"(row0), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap *map, int32_t row0, uint32_t smem_src) {
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(reinterpret_cast<uint64_t>(map)), "r"(8 * kc), "r"(row0), "r"(smem_src + kc * TC5_A_LBO) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool WS>
+__global__ void __launch_bounds__(BT6_THREADS) k_field_backward_tc5v2(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dx,
+                                                                      IrisShadeParams P, int64_t n, const float4 *__restrict__ r5,
+                                                                      const float *__restrict__ d_mat, float *__restrict__ s_out, float *__restrict__ d_mlp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *sX = smem_raw, *sH1 = sX + BT5_TILE_BYTES, *sH2 = sH1 + BT5_TILE_BYTES, *sD = sH2 + BT5_TILE_BYTES, *sDw = sD + BT5_TILE_BYTES;
+    unsigned char *sW1 = sDw + BT5_TILE_BYTES, *sW2 = sW1 + 8192, *sW3 = sW2 + 8192;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sW3 + 2048);                  // [0] MMA rounds, [1] X tile landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2);
+    float *sSc = reinterpret_cast<float *>(tmem_slot + 4);                      // per-row scale s_i of the current tile
+    float *red = sSc + TC5_ROWS;                                                // 8 per-warp maxima
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, half = warp >> 2;                                // TMEM lane quadrant, column half
+    const int row = quad * 32 + lane;                                           // tile row of this thread (two threads per row)
+    const __half *mlp = reinterpret_cast<const __half *>(P.mlp_f16);
+    tc5_stage_weights(mlp, 64, TC5_W_LBO, sW1);
+    tc5_stage_weights(mlp + 4096, 64, TC5_W_LBO, sW2);
+    tc5_stage_weights(mlp + 8192, 16, TC5_W3_LBO, sW3);
+    const int64_t n_tiles = (n + TC5_ROWS - 1) / TC5_ROWS;
+    const uint32_t bar = smem_u32(mbar), bar_x = smem_u32(mbar + 1);
+    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sD), aDw = smem_u32(sDw);
+    const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_x) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((int64_t)blockIdx.x < n_tiles) tma_load_tile(aX, &tm_x, (int32_t)(blockIdx.x * TC5_ROWS), bar_x);      // first X tile
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BT5_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- S: one power of two per CTA with |dy| <= max|d_mat| / 4 <= S for every sample this CTA will see
+    float mx = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * TC5_ROWS + row;
+        if (i < n) {
+            const int k0 = half ? 3 : 0, k1 = half ? 5 : 3;
+            for (int k = k0; k < k1; ++k) {
+                const float v = fabsf(d_mat[5 * i + k]);
+                if (v < __int_as_float(0x7f800000)) mx = fmaxf(mx, v);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mx = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+    float S = 1.f;
+    if (mx > 0.f) {
+        int e;
+        frexpf(mx, &e);                                                          // mx < 2^e
+        S = ldexpf(1.0f, e - 2);                                                 // |dy| <= mx / 4 < S
+    }
+    const float invS = 1.0f / S;
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t id_f64 = umma_idesc_f16(128, 64), id_f16 = umma_idesc_f16(128, 16);                 // forward
+    const uint32_t id_d64 = umma_idesc_f16_major(128, 64, false, true);                                // dgrad: B MN-major
+    const uint32_t id_w64 = umma_idesc_f16_major(64, 64, true, true), id_w16 = umma_idesc_f16_major(64, 16, true, true);   // wgrad
+    const uint32_t row_off = (row >> 3) * TC5_SBO + (row & 7) * 16;
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + 32 * half;     // this warp's lanes, this half's columns
+    const uint32_t chunk0 = 4 * half;                                            // first 16-byte K chunk of this thread's columns
+    uint32_t phase = 0, phase_x = 0;
+    bool first = true;                                                           // first tile of this CTA: dW accumulators start from zero
+    int64_t prev_row0 = -1;                                                      // tile whose dx^ sits in sD, not yet stored
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * TC5_ROWS + row;
+        bool active = false;
+        float dm[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (half == 0 && i < n) {
+            active = true;
+            if (WS) active = __float_as_int(r5[i].w) == -2;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) dm[k] = d_mat[5 * i + k];
+            active = active && (dm[0] != 0.f || dm[1] != 0.f || dm[2] != 0.f || dm[3] != 0.f || dm[4] != 0.f);
+        }
+        float sc = 0.f;
+        // six rounds: 0,1,2 forward layers; 3,4,5 dgrad layers, each together with the wgrad GEMM whose operands are ready by then
+#pragma unroll 1
+        for (int round = 0; round < 6; ++round) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t accw = first ? 0u : 1u;
+                if (round == 0) {
+                    if (prev_row0 >= 0) {                                        // the previous tile's dx^ is complete in sD: send it
+                        tma_store_tile(&tm_dx, (int32_t)prev_row0, aD);
+                    }
+                    mbar_wait(bar_x, phase_x);                                   // this tile's X has landed
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem, umma_desc(aX + 2 * k * TC5_A_LBO, TC5_A_LBO, TC5_SBO), umma_desc(aW1 + 2 * k * TC5_W_LBO, TC5_W_LBO, TC5_SBO), id_f64, k > 0);
+                } else if (round == 1) {
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem, umma_desc(aH1 + 2 * k * TC5_A_LBO, TC5_A_LBO, TC5_SBO), umma_desc(aW2 + 2 * k * TC5_W_LBO, TC5_W_LBO, TC5_SBO), id_f64, k > 0);
+                } else if (round == 2) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // sD (previous dx^) has been read out: this round's epilogue rewrites it
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem, umma_desc(aH2 + 2 * k * TC5_A_LBO, TC5_A_LBO, TC5_SBO), umma_desc(aW3 + 2 * k * TC5_W3_LBO, TC5_W3_LBO, TC5_SBO), id_f16, k > 0);
+                } else if (round == 3) {
+                    // dh2 = dy^ W3 : A = sD chunks 0,1 (K = 16 outputs), B = W3 tile [16 out][64 in] read MN-major (chunk stride 256)
+                    umma_f16(tmem, umma_desc(aD, TC5_A_LBO, TC5_SBO), umma_desc_mn(aW3, TC5_W3_LBO), id_d64, 0u);
+                    // dW3^T (64 x 16) += h2^T dy~ : A = sH2 MN-major (M = 64 features), B = sDw chunks 0,1 MN-major (N = 16), K = 128 samples
+                    for (int k = 0; k < 8; ++k) umma_f16(tmem + 192, umma_desc_mn(aH2 + k * 256, TC5_A_LBO), umma_desc_mn(aDw + k * 256, TC5_A_LBO), id_w16, k > 0 ? 1u : accw);
+                } else if (round == 4) {
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem, umma_desc(aD + 2 * k * TC5_A_LBO, TC5_A_LBO, TC5_SBO), umma_desc_mn(aW2 + k * 256, TC5_W_LBO), id_d64, k > 0);
+                    // dW2 (64 x 64) += dh2~^T h1
+                    for (int k = 0; k < 8; ++k) umma_f16(tmem + 128, umma_desc_mn(aDw + k * 256, TC5_A_LBO), umma_desc_mn(aH1 + k * 256, TC5_A_LBO), id_w64, k > 0 ? 1u : accw);
+                } else {
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem, umma_desc(aD + 2 * k * TC5_A_LBO, TC5_A_LBO, TC5_SBO), umma_desc_mn(aW1 + k * 256, TC5_W_LBO), id_d64, k > 0);
+                    // dW1 (64 x 64) += dh1~^T X
+                    for (int k = 0; k < 8; ++k) umma_f16(tmem + 64, umma_desc_mn(aDw + k * 256, TC5_A_LBO), umma_desc_mn(aX + k * 256, TC5_A_LBO), id_w64, k > 0 ? 1u : accw);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            if (round == 0) phase_x ^= 1u;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (round == 5 && tid == 0) {
+                // every MMA that reads sX is done: request the next tile's X now, under the dx^ epilogue
+                const int64_t nxt = tile + gridDim.x;
+                if (nxt < n_tiles) tma_load_tile(aX, &tm_x, (int32_t)(nxt * TC5_ROWS), bar_x);
+            }
+            if (round <= 1) {
+                // ---- h = relu(acc) -> fp16 -> next layer's A tile
+                unsigned char *dst = (round == 0 ? sH1 : sH2) + row_off;
+                uint32_t r[32];
+                TC5_LD32(r, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 v;
+                    v.x = pack_relu_f16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                    v.y = pack_relu_f16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                    v.z = pack_relu_f16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                    v.w = pack_relu_f16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                    *reinterpret_cast<uint4 *>(dst + (chunk0 + c) * TC5_A_LBO) = v;
+                }
+            } else if (round == 2) {
+                // ---- dy = d_mat * d(mat)/dy, per-sample power-of-two normalisation (field.cuh, k_field_backward_dgrad); warps 0..3 only
+                if (half == 0) {
+                    uint32_t r[16];
+                    TC5_LD16(r, taddr);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float dy[5], mxy = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float yk = __half2float(__float2half_rn(__uint_as_float(r[k])));
+                        const float s = 1.0f / (1.0f + expf(-yk));
+                        dy[k] = active ? dm[k] * (k == 3 ? 0.98f : 1.0f) * s * (1.0f - s) : 0.f;
+                        mxy = fmaxf(mxy, fabsf(dy[k]));
+                    }
+                    sc = 0.f;
+                    if (mxy > 0.f && mxy < __int_as_float(0x7f800000)) {
+                        int e;
+                        frexpf(mxy, &e);
+                        sc = ldexpf(1.0f, e);
+                    }
+                    const float inv = sc > 0.f ? 1.0f / sc : 0.f;
+                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                    uint4 hd, hw;
+                    hd.x = pack_f16x2(dy[0] * inv, dy[1] * inv); hd.y = pack_f16x2(dy[2] * inv, dy[3] * inv); hd.z = pack_f16x2(dy[4] * inv, 0.f); hd.w = 0u;
+                    hw.x = pack_f16x2(dy[0] * invS, dy[1] * invS); hw.y = pack_f16x2(dy[2] * invS, dy[3] * invS); hw.z = pack_f16x2(dy[4] * invS, 0.f); hw.w = 0u;
+                    *reinterpret_cast<uint4 *>(sD + row_off) = hd;
+                    *reinterpret_cast<uint4 *>(sD + TC5_A_LBO + row_off) = zero;
+                    *reinterpret_cast<uint4 *>(sDw + row_off) = hw;
+                    *reinterpret_cast<uint4 *>(sDw + TC5_A_LBO + row_off) = zero;
+                    sSc[row] = sc;
+                    if (i < n) s_out[i] = sc;
+                }
+            } else if (round == 3 || round == 4) {
+                // ---- dh^ = acc . relu'(h) -> fp16 -> sD (next dgrad A operand) and, rescaled by s_i / S, -> sDw (wgrad operand)
+                const unsigned char *hsrc = (round == 3 ? sH2 : sH1) + row_off;
+                const __half2 ws2 = __float2half2_rn(sSc[row] * invS);
+                uint32_t r[32];
+                TC5_LD32(r, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 h = *reinterpret_cast<const uint4 *>(hsrc + (chunk0 + c) * TC5_A_LBO);
+                    uint4 hd, hw;
+                    hd.x = pack_f16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1])) & relu_mask_f16x2(h.x);
+                    hd.y = pack_f16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])) & relu_mask_f16x2(h.y);
+                    hd.z = pack_f16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])) & relu_mask_f16x2(h.z);
+                    hd.w = pack_f16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])) & relu_mask_f16x2(h.w);
+                    hw.x = hmul2_u32(hd.x, ws2); hw.y = hmul2_u32(hd.y, ws2); hw.z = hmul2_u32(hd.z, ws2); hw.w = hmul2_u32(hd.w, ws2);
+                    *reinterpret_cast<uint4 *>(sD + (chunk0 + c) * TC5_A_LBO + row_off) = hd;
+                    *reinterpret_cast<uint4 *>(sDw + (chunk0 + c) * TC5_A_LBO + row_off) = hw;
+                }
+            } else {
+                // ---- dx^ (normalised) -> fp16 -> sD in the tile layout; one bulk tensor store sends it at the next synchronisation point
+                uint32_t r[32];
+                TC5_LD32(r, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 v;
+                    v.x = pack_f16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                    v.y = pack_f16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                    v.z = pack_f16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                    v.w = pack_f16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                    *reinterpret_cast<uint4 *>(sD + (chunk0 + c) * TC5_A_LBO + row_off) = v;
+                }
+            }
+        }
+        prev_row0 = tile * TC5_ROWS;
+        first = false;
+    }
+    // ---- last dx^ tile, then drain the weight-gradient accumulators: M = 64 rows live in TMEM lanes 32 (m / 16) + m % 16
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && prev_row0 >= 0) tma_store_tile(&tm_dx, (int32_t)prev_row0, aD);
+    if (!first && half == 0) {
+        const int m = 16 * quad + lane;                                          // feature row held by this lane (lanes < 16)
+        const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16);
+        for (int blk = 0; blk < 3; ++blk) {                                      // dW1, dW2, dW3^T
+            const int ncol = blk == 2 ? 16 : 64;
+            for (int q = 0; q < ncol / 16; ++q) {
+                uint32_t r[16];
+                BT5_LD16(r, tbase + 64 * (blk + 1), q);                          // all lanes take part in the load (warp-collective)
+                if (lane < 16) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float v = __uint_as_float(r[k]) * S;
+                        if (v != 0.f) {
+                            if (blk == 0) atomicAdd(d_mlp + m * 64 + 16 * q + k, v);                       // dW1[out m][in]
+                            else if (blk == 1) atomicAdd(d_mlp + 4096 + m * 64 + 16 * q + k, v);            // dW2[out m][in]
+                            else atomicAdd(d_mlp + 8192 + (16 * q + k) * 64 + m, v);                       // dW3[out][in m] (accumulated transposed)
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the store has left shared memory (and is globally visible) before the CTA exits
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BT5_TMEM_COLS) : "memory");
+}

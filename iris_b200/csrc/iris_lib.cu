@@ -12,6 +12,7 @@
 #include "field.cuh"
 #include "field_tc5.cuh"
 #include "field_bwd_tc5.cuh"
+#include "field_bwd_tc5v2.cuh"
 #include "kernels.cuh"
 #include "wavefront.cuh"
 #include "crf.cuh"
@@ -80,7 +81,7 @@ static int g_sm_count = 0;
 static int g_tc5_ctas = 4;      // tcgen05 kernel: CTAs per SM (34.9 KB smem, 64 TMEM columns each)
 static int g_single_impl = 1;      // 1: wavefront bounce (k_single_gen -> k_trace_queue -> k_single_shade), 0: fused k_bounce_single
 static int64_t g_single_chunk = 8 << 20;   // samples per wavefront chunk
-static int g_field_bwd_impl = 1;   // 1: fused tcgen05 dgrad + wgrad kernel (field_bwd_tc5.cuh; used whenever the encoded inputs are available); 0: dgrad (mma.sync) + wgrad (TF32 split-K) kernels
+static int g_field_bwd_impl = 2;   // 1: fused tcgen05 dgrad + wgrad kernel (field_bwd_tc5.cuh; used whenever the encoded inputs are available); 0: dgrad (mma.sync) + wgrad (TF32 split-K) kernels
 static int g_bake_impl = 2;        // 2: persistent warps with the generator / radiance lookup in the kernel (k_bake_persistent, default: +20-44 % over 0
                                    //    except on mirror-like lobes), 0: fused k_bake with block-level direction sort, 1: through the ray queue
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
@@ -105,6 +106,29 @@ static int ensure_device_setup(int device) {
     g_sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaFuncSetAttribute(k_single_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * IRIS_BWD_KMAX * IRIS_BLOCK * 4));
     g_field_ready[device] = true;
+    return IRIS_OK;
+}
+
+// ---- TMA tensor map over a row-major [rows][64] fp16 array with 8-column x 128-row boxes (field_bwd_tc5v2.cuh).  The encoder is a
+//      driver-API entry point, fetched through the runtime so that the library does not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_tile_map(CUtensorMap *out, const void *base, int64_t rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(IRIS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {8, 128};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IRIS_ERR_CUDA, "cuTensorMapEncodeTiled failed (status " + std::to_string((int)r) + ")");
     return IRIS_OK;
 }
 
@@ -225,7 +249,7 @@ int iris_set_option(const char *name, int value) {
         CUDA_TRY(cudaFuncSetAttribute(k_bake<1>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
         return IRIS_OK;
     }
-    if (name && std::strcmp(name, "field_backward_impl") == 0 && (value == 0 || value == 1)) { g_field_bwd_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "field_backward_impl") == 0 && value >= 0 && value <= 2) { g_field_bwd_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "wave_impl") == 0 && (value == 0 || value == 1)) { g_wave_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "bake_impl") == 0 && value >= 0 && value <= 2) { g_bake_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
@@ -565,8 +589,23 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
         if (x_saved) act.X = x_saved + 64 * c0;        // encoded inputs kept by the forward pass: not recomputed, not copied
         const int64_t tiles = (m + FIELD_BWD_BLOCK - 1) / FIELD_BWD_BLOCK;
         const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * (512 / FIELD_BWD_BLOCK));
-        const bool fused = g_field_bwd_impl == 1 && x_saved != nullptr;          // one-kernel dgrad + wgrad on tcgen05 (field_bwd_tc5.cuh)
-        if (fused) {
+        const bool fused = g_field_bwd_impl >= 1 && x_saved != nullptr;          // one-kernel dgrad + wgrad on tcgen05 (field_bwd_tc5.cuh / field_bwd_tc5v2.cuh)
+        if (fused && g_field_bwd_impl == 2) {
+            static bool fattr2[64] = {false};
+            if (!fattr2[cur_dev & 63]) {
+                CUDA_TRY(cudaFuncSetAttribute(k_field_backward_tc5v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT6_SMEM_BYTES));
+                CUDA_TRY(cudaFuncSetAttribute(k_field_backward_tc5v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT6_SMEM_BYTES));
+                fattr2[cur_dev & 63] = true;
+            }
+            CUtensorMap tm_x, tm_dx;
+            int rc2 = make_row_tile_map(&tm_x, act.X, m);
+            if (rc2 == IRIS_OK) rc2 = make_row_tile_map(&tm_dx, act.dx, m);
+            if (rc2) return rc2;
+            ProfScope ps(K_FIELD_BACKWARD_TC5, st);
+            const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * 2);
+            if (r5) k_field_backward_tc5v2<true><<<gf, BT6_THREADS, BT6_SMEM_BYTES, st>>>(tm_x, tm_dx, *P, m, r5 + c0, d_mat + 5 * c0, act.s, d_params);
+            else k_field_backward_tc5v2<false><<<gf, BT6_THREADS, BT6_SMEM_BYTES, st>>>(tm_x, tm_dx, *P, m, nullptr, d_mat + 5 * c0, act.s, d_params);
+        } else if (fused) {
             static bool fattr[64] = {false};
             if (!fattr[cur_dev & 63]) {
                 CUDA_TRY(cudaFuncSetAttribute(k_field_backward_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT5_SMEM_BYTES));
