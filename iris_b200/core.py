@@ -298,8 +298,9 @@ def single_forward(scene, tables, rays, spp, sampler, want_record=False, workspa
     return L, record
 
 
-def single_backward(tables, dL, spp, record, want_radiance=True, d_params=None, workspace=None):
-    """Adjoint of path_tracing_single: returns d_radiance (K,3) (accumulated from zero)."""
+def single_backward(tables, dL, spp, record, want_radiance=True, d_params=None, workspace=None, encoded=None):
+    """Adjoint of path_tracing_single: returns d_radiance (K,3) (accumulated from zero).  encoded: the array the forward kept
+    (default: the one travelling with the record as `record.encoded`)."""
     dL = dL.contiguous().float()
     B = dL.shape[0]
     dev = dL.device
@@ -310,7 +311,8 @@ def single_backward(tables, dL, spp, record, want_radiance=True, d_params=None, 
         workspace = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
     P = tables.c()
     with torch.cuda.device(dev):
-        C.check(lib.iris_single_backward(ctypes.byref(P), C.ptr(dL), B, int(spp), C.ptr(record), C.ptr(getattr(record, "encoded", None)), C.ptr(d_rad), C.ptr(d_params),
+        enc = encoded if encoded is not None else getattr(record, "encoded", None)
+        C.check(lib.iris_single_backward(ctypes.byref(P), C.ptr(dL), B, int(spp), C.ptr(record), C.ptr(enc), C.ptr(d_rad), C.ptr(d_params),
                                          C.ptr(workspace), 0 if workspace is None else workspace.numel(), C.stream_ptr()))
     return d_rad
 

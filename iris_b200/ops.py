@@ -4,8 +4,9 @@
    object that carries the reference's buffers -- the reference's own `SLFEmitter` / `NGPBRDF` instances or the mirrors in
    `iris_b200.model` (duck typing on `is_emitter`, `emitter_vertices`, `emitter_area`, `radiance`, `slf.inds`, `slf.radiance`,
    `slf.voxel_min/max`, `mlp.params`, `voxel_min/max`).
- * `PathTracingSingle` is the `torch.autograd.Function` that ties `iris_single_forward` to `iris_single_backward`: gradients
-   flow to `emitter_net.radiance` (rows [0,K), the reference's quirk) and to `material_net.mlp.params`.
+ * the estimators, the field and the ray cast go through `torch.ops.iris_b200.*` (iris_b200/library.py: torch.library custom ops with
+   schemas, fake implementations and registered adjoints over the same C ABI): gradients flow to `emitter_net.radiance` (rows
+   [0,K), the reference's quirk) and to `material_net.mlp.params`.
  * uniforms: Philox keyed by a seed drawn from torch's global generator per call (reproducible under `torch.manual_seed`,
    like the reference's `torch.rand`), or an explicit `(N,D)` buffer via `iris_b200.ops.inject_samples(U)` for parity runs.
 """
@@ -19,6 +20,7 @@ import torch
 
 from . import _capi as C
 from . import core
+from . import library as L_
 
 _INJECT = []
 
@@ -90,35 +92,21 @@ def ray_intersect(scene, xs, ds):
     """utils/path_tracing.py:17-48: positions, normals (flipped toward -ds), uvs, idx (int64, -1 = miss), valid."""
     sc = as_scene(scene)
     shape = xs.shape[:-1]
-    t, prim, uv, p, n = sc.intersect_raw(xs.reshape(-1, 3), ds.reshape(-1, 3))
+    t, prim, uv, p, n = torch.ops.iris_b200.intersect(L_.handle(sc), xs.reshape(-1, 3).contiguous().float(), ds.reshape(-1, 3).contiguous().float())
     idx = prim.long()
     return p.reshape(*shape, 3), n.reshape(*shape, 3), uv.reshape(*shape, 2), idx.reshape(shape), (idx >= 0).reshape(shape)
 
 
 # ------------------------------------------------------------------------------------------------ path_tracing_single
-class PathTracingSingle(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, radiance, params, scene, tables, rays, spp, sampler):
-        need_rad = radiance is not None and radiance.requires_grad
-        need_par = params is not None and params.requires_grad
-        L, rec = core.single_forward(scene, tables, rays, spp, sampler, want_record=need_rad or need_par, want_encoded=need_par)
-        ctx.tables, ctx.spp, ctx.rec = tables, spp, rec
-        ctx.need = (need_rad, need_par)
-        ctx.shapes = (None if radiance is None else radiance.shape, None if params is None else params.shape)
-        return L
-
-    @staticmethod
-    def backward(ctx, dL):
-        need_rad, need_par = ctx.need
-        d_rad = d_par = None
-        if ctx.rec is not None and (need_rad or need_par):
-            if need_par:
-                d_par = torch.zeros(ctx.shapes[1], device=dL.device, dtype=torch.float32)
-            g = core.single_backward(ctx.tables, dL, ctx.spp, ctx.rec, want_radiance=need_rad, d_params=d_par)
-            if need_rad:
-                d_rad = torch.zeros(ctx.shapes[0], device=dL.device, dtype=torch.float32)      # (F,3): only rows [0,K) receive gradient
-                d_rad[:ctx.tables.K] = g
-        return d_rad, d_par, None, None, None, None, None
+def _single(scene, tables, radiance, params, rays, spp, sampler):
+    """torch.ops.iris_b200.single_forward (iris_b200/library.py): forward kernel + registered replay adjoint.  Gradients flow to
+    `radiance` (rows [0,K), the reference's quirk) and to `params` (material_net.mlp.params)."""
+    need_rad = radiance is not None and radiance.requires_grad and torch.is_grad_enabled()
+    need_par = params is not None and params.requires_grad and torch.is_grad_enabled()
+    rec_mode = 2 if need_par else (1 if need_rad else 0)
+    L, _, _ = torch.ops.iris_b200.single_forward(radiance, params, rays, L_.handle(scene), L_.handle(tables), int(spp), sampler.seed, sampler.lane_offset,
+                                                 sampler.U, rec_mode)
+    return L
 
 
 def pack_rays(rays_o, rays_d, dx_du, dy_dv):
@@ -130,14 +118,15 @@ def path_tracing_single(scene, emitter_net, material_net, rays_o, rays_d, dx_du,
     sc = as_scene(scene)
     T = tables_for(emitter_net, material_net, rays_o.device)
     params = material_net.mlp.params if hasattr(material_net, "mlp") else None
-    return PathTracingSingle.apply(emitter_net.radiance, params, sc, T, pack_rays(rays_o, rays_d, dx_du, dy_dv), int(spp), next_sampler(rays_o.device))
+    return _single(sc, T, emitter_net.radiance, params, pack_rays(rays_o, rays_d, dx_du, dy_dv), spp, next_sampler(rays_o.device))
 
 
 def path_tracing(scene, emitter_net, material_net, rays_o, rays_d, dx_du, dy_dv, spp, indir_depth):
     """utils/path_tracing.py:214-318.  Forward only: the reference itself calls it under no_grad (render.py:171-176,
     train_brdf_crf.py:360-370) and detaches everything past the first bounce (:313-315)."""
     T = tables_for(emitter_net, material_net, rays_o.device)
-    return core.path_tracing(as_scene(scene), T, pack_rays(rays_o, rays_d, dx_du, dy_dv), spp, indir_depth, next_sampler(rays_o.device))
+    smp = next_sampler(rays_o.device)
+    return torch.ops.iris_b200.path_tracing(pack_rays(rays_o, rays_d, dx_du, dy_dv), L_.handle(as_scene(scene)), L_.handle(T), int(spp), int(indir_depth), smp.seed, smp.U)
 
 
 def path_tracing_det(scene, emitter_net, material_net, roughness_level, positions, wis, normals, triangle_idxs, spp, indir_depth):
@@ -163,42 +152,27 @@ def trace_indirect(scene, emitter_net, material_net, position, wo, normal, indir
 def bake_diffuse(scene, emitter_net, position, normal, spp):
     """The chunk loop of bake_shading.py:105-123 as one launch: Ld (B,3)."""
     T = tables_for(emitter_net, None, position.device)
-    return core.bake(as_scene(scene), T, 0, 1.0, position, normal, None, spp, next_sampler(position.device))
+    smp = next_sampler(position.device)
+    return torch.ops.iris_b200.bake(position.contiguous().float(), normal.contiguous().float(), None, L_.handle(as_scene(scene)), L_.handle(T), 0, 1.0, int(spp),
+                                    smp.seed, smp.U)[0]
 
 
 def bake_specular(scene, emitter_net, position, wo, normal, roughness, spp):
     """The chunk loop of bake_shading.py:165-188 for one roughness level: (Ls0, Ls1)."""
     T = tables_for(emitter_net, None, position.device)
-    return core.bake(as_scene(scene), T, 1, float(roughness), position, normal, wo, spp, next_sampler(position.device))
+    smp = next_sampler(position.device)
+    return torch.ops.iris_b200.bake(position.contiguous().float(), normal.contiguous().float(), wo.contiguous().float(), L_.handle(as_scene(scene)), L_.handle(T),
+                                    1, float(roughness), int(spp), smp.seed, smp.U)
 
 
 # ------------------------------------------------------------------------------------------------ BRDF field
-class FieldForward(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, params, tables, position):
-        ctx.tables = tables
-        ctx.n_params = params.numel()
-        if params.requires_grad:
-            mat, enc = core.field_forward(tables, position, want_encoded=True)      # the adjoint reuses the encoded inputs
-            ctx.save_for_backward(position, enc)
-            return mat
-        ctx.save_for_backward(position, None)
-        return core.field_forward(tables, position)
-
-    @staticmethod
-    def backward(ctx, d_mat):
-        position, enc = ctx.saved_tensors
-        d = torch.zeros(ctx.n_params, device=d_mat.device, dtype=torch.float32)
-        core.field_backward(ctx.tables, position, d_mat, d, encoded=enc)
-        return d, None, None
-
-
 def field(material_net, position):
     """NGPBRDF.forward (model/brdf.py:243-260): dict(albedo (N,3), roughness (N,1), metallic (N,1))."""
     T = _field_tables(material_net, position.device)
     p = material_net.mlp.params
     shape = position.shape[:-1]
-    mat = FieldForward.apply(p, T, position.reshape(-1, 3).float().contiguous())
+    keep = bool(p.requires_grad and torch.is_grad_enabled())            # the adjoint reuses the encoded inputs
+    mat, _ = torch.ops.iris_b200.field_forward(p, position.reshape(-1, 3).float().contiguous(), L_.handle(T), keep)
     return {"albedo": mat[:, 0:3].reshape(*shape, 3), "roughness": mat[:, 3:4].reshape(*shape, 1), "metallic": mat[:, 4:5].reshape(*shape, 1)}
 
 
