@@ -120,14 +120,16 @@ __global__ void __launch_bounds__(BT6_THREADS) k_field_backward_tc5v2(const __gr
     // ---- S: one power of two per CTA with |dy| <= max|d_mat| / 4 <= S for every sample this CTA will see
     float mx = 0.f;
     if (!is_mma_warp) {
+        // (a streaming pass over the CTA's share of d_mat: unrolled so that several tiles' loads are in flight)
+        const int k0 = half ? 3 : 0;
+#pragma unroll 4
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t i = tile * TC5_ROWS + row;
             if (i < n) {
-                const int k0 = half ? 3 : 0, k1 = half ? 5 : 3;
-                for (int k = k0; k < k1; ++k) {
-                    const float v = fabsf(d_mat[5 * i + k]);
-                    if (v < __int_as_float(0x7f800000)) mx = fmaxf(mx, v);
-                }
+                const float v0 = fabsf(__ldg(d_mat + 5 * i + k0)), v1 = fabsf(__ldg(d_mat + 5 * i + k0 + 1)), v2 = half ? 0.f : fabsf(__ldg(d_mat + 5 * i + 2));
+                if (v0 < __int_as_float(0x7f800000)) mx = fmaxf(mx, v0);
+                if (v1 < __int_as_float(0x7f800000)) mx = fmaxf(mx, v1);
+                if (v2 < __int_as_float(0x7f800000)) mx = fmaxf(mx, v2);
             }
         }
     }
@@ -234,17 +236,16 @@ __global__ void __launch_bounds__(BT6_THREADS) k_field_backward_tc5v2(const __gr
         uint32_t phase = 0;
         // d_mat row (and the "sample is live" flag) of the tile after the current one are fetched a tile ahead
         float dm_n[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        bool act_n = false;
+        int code_n = -1;                                                         // raw "lane state" word of the record (-2 = live): compared a tile later
         auto fetch = [&](int64_t tile) {
             const int64_t i = tile * TC5_ROWS + row;
-            act_n = false;
+            code_n = -1;
 #pragma unroll
             for (int k = 0; k < 5; ++k) dm_n[k] = 0.f;
             if (tile < n_tiles && i < n) {
-                act_n = true;
-                if (WS) act_n = __float_as_int(r5[i].w) == -2;
+                code_n = WS ? __float_as_int(__ldg(reinterpret_cast<const float *>(r5 + i) + 3)) : -2;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) dm_n[k] = d_mat[5 * i + k];
+                for (int k = 0; k < 5; ++k) dm_n[k] = __ldg(d_mat + 5 * i + k);
             }
         };
         fetch(blockIdx.x);
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(BT6_THREADS) k_field_backward_tc5v2(const __gr
             float dm[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) dm[k] = dm_n[k];
-            const bool active = act_n && (dm[0] != 0.f || dm[1] != 0.f || dm[2] != 0.f || dm[3] != 0.f || dm[4] != 0.f);
+            const bool active = code_n == -2 && (dm[0] != 0.f || dm[1] != 0.f || dm[2] != 0.f || dm[3] != 0.f || dm[4] != 0.f);
             fetch(tile + gridDim.x);
             float sc = 0.f;
 #pragma unroll 1
