@@ -273,6 +273,8 @@ int64_t iris_launch_count(void);
  *   "single_impl"             1 wavefront bounce (generate -> persistent ray-queue trace -> shade) | 0 one fused kernel
  *   "single_chunk_log2"       23: samples per ray-queue chunk = 2^value (10..30)
  *   "wave_impl"               1 path_tracing / det / indirect bounces through the ray queue | 0 fused bounce kernel
+ *   "wave_compact"            1 live-lane lists per bounce (dense ray queue / hit records, kernels exit past the device-side count: the reference's
+ *                             lane compaction, utils/path_tracing.py:347-352,492-501) | 0 every bounce kernel over all lanes
  *   "bake_impl"               2 persistent kernel, generator and radiance lookup inside | 0 fused kernel with block-level direction sort | 1 ray queue
  *   "intersect_impl"          0 one ray per lane (best on camera rays) | 1 persistent warps with dynamic ray fetch (best on incoherent rays)
  *   "persist_ctas_per_sm"     8: resident CTAs per SM of the persistent kernels (1..16)

@@ -267,7 +267,8 @@ __device__ __forceinline__ void warp_tile_to_global(const __half *Xs, __half *ds
 template <bool WS>
 __global__ void __launch_bounds__(IRIS_BLOCK) k_field_forward(IrisShadeParams P, int64_t n, const float *__restrict__ position, float *__restrict__ mat,
                                                                const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2,
-                                                               __half *__restrict__ x_save, int pair) {
+                                                               __half *__restrict__ x_save, int pair, const unsigned long long *__restrict__ n_dev) {
+    if (n_dev != nullptr) n = min(n, (int64_t)*n_dev);         // rows counted on the device (live lanes of a wavefront bounce)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half *Wsm = reinterpret_cast<__half *>(smem_raw);
     __half *Xs = Wsm + (64 + 64 + 16) * FIELD_LD + (threadIdx.x >> 5) * 32 * FIELD_LD;

@@ -62,7 +62,8 @@ __device__ int g_tc5_debug = 0;   // 0 normal, 1 skip the encode, 2 skip the MLP
 template <bool WS>
 __global__ void __launch_bounds__(TC5_ROWS) k_field_forward_tc5(IrisShadeParams P, int64_t n, const float *__restrict__ position, float *__restrict__ mat,
                                                                  const float4 *__restrict__ w0, float4 *__restrict__ w1, float4 *__restrict__ w2,
-                                                                 __half *__restrict__ x_save, int pair) {
+                                                                 __half *__restrict__ x_save, int pair, const unsigned long long *__restrict__ n_dev) {
+    if (n_dev != nullptr) n = min(n, (int64_t)*n_dev);         // rows counted on the device (live lanes of a wavefront bounce)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sA = smem_raw;
     unsigned char *sW1 = sA + TC5_A_BYTES, *sW2 = sW1 + 8192, *sW3 = sW2 + 8192;

@@ -85,6 +85,7 @@ static int g_field_bwd_impl = 2;   // 1: fused tcgen05 dgrad + wgrad kernel (fie
 static int g_bake_impl = 2;        // 2: persistent warps with the generator / radiance lookup in the kernel (k_bake_persistent, default: +20-44 % over 0
                                    //    except on mirror-like lobes), 0: fused k_bake with block-level direction sort, 1: through the ray queue
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
+static int g_wave_compact = 1;     // 1: live-lane lists (dense queues, dead lanes cost nothing), 0: every kernel over all lanes (A/B)
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
 static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
 static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
@@ -251,6 +252,7 @@ int iris_set_option(const char *name, int value) {
     }
     if (name && std::strcmp(name, "field_backward_impl") == 0 && value >= 0 && value <= 2) { g_field_bwd_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "wave_impl") == 0 && (value == 0 || value == 1)) { g_wave_impl = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "wave_compact") == 0 && (value == 0 || value == 1)) { g_wave_compact = value; return IRIS_OK; }
     if (name && std::strcmp(name, "bake_impl") == 0 && value >= 0 && value <= 2) { g_bake_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
@@ -503,7 +505,7 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
         {
             ProfScope ps(K_TRACE_QUEUE, st);
             const int grid = (int)std::min<int64_t>(blocks_for(nc), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
-            k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, nc, 0, hit, counters + chunk);
+            k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, nc, 0, hit, counters + chunk, nullptr, 0);
         }
         LAUNCHED();
         {
@@ -518,7 +520,7 @@ int iris_bake(const IrisScene *s, const IrisShadeParams *P, int mode, float roug
 }
 
 static int launch_field(const IrisShadeParams *P, int64_t n, const float *position, float *mat, const float4 *w0, float4 *w1, float4 *w2, cudaStream_t st,
-                        __half *x_save = nullptr, int pair = 1) {
+                        __half *x_save = nullptr, int pair = 1, const unsigned long long *n_dev = nullptr) {
     static bool attr_done_dev[64] = {false};       // function attributes belong to the device context: set them once per device
     int cur_dev = 0;
     CUDA_TRY(cudaGetDevice(&cur_dev));
@@ -542,11 +544,11 @@ static int launch_field(const IrisShadeParams *P, int64_t n, const float *positi
     ProfScope ps(K_FIELD_FORWARD, st);
     if (g_field_impl == 1) {
         const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)g_sm_count * g_tc5_ctas);
-        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
-        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
+        if (w0) k_field_forward_tc5<true><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair, n_dev);
+        else k_field_forward_tc5<false><<<g5, TC5_ROWS, TC5_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair, n_dev);
     } else {
-        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
-        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair);
+        if (w0) k_field_forward<true><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair, n_dev);
+        else k_field_forward<false><<<grid, IRIS_BLOCK, FIELD_SMEM_BYTES, st>>>(*P, n, position, mat, w0, w1, w2, x_save, pair, n_dev);
     }
     LAUNCHED();
     return IRIS_OK;
@@ -719,7 +721,7 @@ int iris_single_forward(const IrisScene *s, const IrisShadeParams *P, const floa
         {
             ProfScope ps(K_TRACE_QUEUE, st);
             const int grid = (int)std::min<int64_t>(blocks_for(2 * nc), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
-            k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, 2 * nc, nc, hit, counters + chunk);
+            k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, 2 * nc, nc, hit, counters + chunk, nullptr, 0);
         }
         LAUNCHED();
         {
@@ -774,10 +776,31 @@ int iris_single_backward(const IrisShadeParams *P, const float *dL, int64_t n_pi
 }
 
 // ------------------------------------------------------------------------------------------------ wavefront estimators
-int64_t iris_wave_workspace_bytes(int64_t n_lanes) { return WAVE_STREAMS * 16 * std::max<int64_t>(n_lanes, 1); }
+int64_t iris_wave_workspace_bytes(int64_t n_lanes) { return WAVE_STREAMS * 16 * std::max<int64_t>(n_lanes, 1) + WAVE_TAIL_BYTES; }
 
-static int wave_field(const IrisShadeParams *P, int64_t n, float4 *pos, float4 *m1, float4 *m2, cudaStream_t st) {
-    return launch_field(P, n, nullptr, nullptr, pos, m1, m2, st);
+// The live-lane lists of one estimator call (wavefront.cuh): `cur` feeds bounce k, the shade kernel appends the survivors to `next`.
+struct WaveLanes {
+    int32_t *cur = nullptr, *next = nullptr;
+    unsigned long long *cnt = nullptr;      // cnt[k]: lanes entering bounce k
+    int k = 0;
+    bool on = false;
+    const int32_t *idx() const { return on ? cur : nullptr; }
+    const unsigned long long *count() const { return on ? cnt + k : nullptr; }
+    int32_t *idx_next() const { return on ? next : nullptr; }
+    unsigned long long *count_next() const { return on ? cnt + k + 1 : nullptr; }
+    void advance() { std::swap(cur, next); ++k; }
+};
+static WaveLanes wave_lanes(const WaveState &W) {
+    WaveLanes L;
+    L.on = g_wave_impl == 1 && g_wave_compact == 1;       // the fused bounce kernel (wave_impl 0) works on all lanes in place
+    L.cur = W.idxA;
+    L.next = W.idxB;
+    L.cnt = W.cnt;
+    return L;
+}
+
+static int wave_field(const IrisShadeParams *P, int64_t n, float4 *pos, float4 *m1, float4 *m2, cudaStream_t st, const unsigned long long *n_dev = nullptr) {
+    return launch_field(P, n, nullptr, nullptr, pos, m1, m2, st, nullptr, 1, n_dev);
 }
 
 // one "bounce a" of the wavefront estimators: fused kernel (wave_impl 0) or generate -> ray-queue trace -> resolve (default)
@@ -789,7 +812,7 @@ static int wave_field(const IrisShadeParams *P, int64_t n, float4 *pos, float4 *
     default: KERNEL<3><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(__VA_ARGS__); break;              \
     }
 static int wave_bounce_a(int kind, const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int col0, float level, int64_t n, WaveState W,
-                         cudaStream_t st) {
+                         const WaveLanes &L, cudaStream_t st) {
     if (g_wave_impl == 0) {
         ProfScope ps(K_WAVE_A, st);
         WAVE_KIND_SWITCH(k_wave_bounce_a, view_of(s), *P, *smp, col0, level, n, W)
@@ -799,40 +822,47 @@ static int wave_bounce_a(int kind, const IrisScene *s, const IrisShadeParams *P,
     CUDA_TRY(cudaMemsetAsync(W.counter, 0, 8, st));
     {
         ProfScope ps(K_WAVE_A, st);
-        WAVE_KIND_SWITCH(k_wave_gen, *P, *smp, col0, level, n, W)
+        WAVE_KIND_SWITCH(k_wave_gen, *P, *smp, col0, level, n, W, L.idx(), L.count())
     }
     LAUNCHED();
     {
         ProfScope ps(K_TRACE_QUEUE, st);
-        const bool shadow = kind <= 1;                       // det_*: only the closest-hit half of the queue is populated
-        const float4 *ro = shadow ? W.RO : W.RO + n, *rd = shadow ? W.RD : W.RD + n;
-        float4 *hit = shadow ? W.HIT : W.HIT + n;
+        const bool shadow = kind <= 1;                       // det_*: only closest-hit rays, in the first part of the queue
         const int64_t nr = shadow ? 2 * n : n;
         const int grid = (int)std::min<int64_t>(blocks_for(nr), (int64_t)g_persist_ctas * (g_sm_count > 0 ? g_sm_count : 148));
-        k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), ro, rd, nr, shadow ? n : 0, hit, W.counter);
+        k_trace_queue<<<grid, IRIS_BLOCK, 0, st>>>(view_of(s), W.RO, W.RD, nr, shadow ? n : 0, W.HIT, W.counter, L.count(), shadow ? 2 : 1);
     }
     LAUNCHED();
     {
         ProfScope ps(K_WAVE_A, st);
-        WAVE_KIND_SWITCH(k_wave_resolve, view_of(s), n, W)
+        WAVE_KIND_SWITCH(k_wave_resolve, view_of(s), n, W, L.idx(), L.count())
     }
     LAUNCHED();
     return IRIS_OK;
 }
 
-// one indirect depth (trace_indirect loop body) on the current state
-static int wave_indirect(const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int64_t n, WaveState W, int depth, int col_base,
+// field at the hits + radiance / MIS / state update of one bounce; advances the live-lane list
+static int wave_bounce_b(int kind, const IrisShadeParams *P, int64_t n, WaveState W, WaveLanes &L, cudaStream_t st) {
+    int rc = wave_field(P, n, W.H0, W.M1, W.M2, st, L.count());
+    if (rc) return rc;
+    {
+        ProfScope ps(K_WAVE_B, st);
+        if (kind == 0) k_wave_bounce_b<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W, L.idx(), L.count(), L.idx_next(), L.count_next());
+        else if (kind == 1) k_wave_bounce_b<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W, L.idx(), L.count(), L.idx_next(), L.count_next());
+        else k_wave_bounce_b<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W, L.idx(), L.count(), L.idx_next(), L.count_next());
+    }
+    LAUNCHED();
+    if (L.on) L.advance();
+    return IRIS_OK;
+}
+
+// indirect depths (trace_indirect loop body) on the current state
+static int wave_indirect(const IrisScene *s, const IrisShadeParams *P, const IrisSampler *smp, int64_t n, WaveState W, WaveLanes &L, int depth, int col_base,
                          cudaStream_t st) {
     for (int k = 0; k < depth; ++k) {
-        int rc = wave_bounce_a(1, s, P, smp, col_base + 6 * k, 0.f, n, W, st);
+        int rc = wave_bounce_a(1, s, P, smp, col_base + 6 * k, 0.f, n, W, L, st);
         if (rc) return rc;
-        rc = wave_field(P, n, W.H0, W.M1, W.M2, st);
-        if (rc) return rc;
-        {
-            ProfScope ps(K_WAVE_B, st);
-            k_wave_bounce_b<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W);
-        }
-        LAUNCHED();
+        if ((rc = wave_bounce_b(1, P, n, W, L, st))) return rc;
     }
     return IRIS_OK;
 }
@@ -843,6 +873,8 @@ static int wave_check(const IrisScene *s, const IrisShadeParams *P, const IrisSa
     int rc = check_params(P, true);
     if (rc) return rc;
     if (n_rows < 0 || spp <= 0 || depth < 0 || !smp) return fail(IRIS_ERR_INVALID, "bad arguments");
+    if (depth + 2 > WAVE_MAX_BOUNCES) return fail(IRIS_ERR_INVALID, "indir_depth too large");
+    if (n_rows * (int64_t)spp > 0x7FFFFFFFll) return fail(IRIS_ERR_INVALID, "too many lanes for one call (rows * spp must fit 31 bits)");
     if (smp->U && smp->stride < need_cols) return fail(IRIS_ERR_INVALID, "sampler stride too small for this estimator / depth");
     if (n_rows > 0 && (!ws || ws_bytes < iris_wave_workspace_bytes(n_rows * spp))) return fail(IRIS_ERR_WORKSPACE, "workspace too small");
     if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(IRIS_ERR_INVALID, "workspace must be 16-byte aligned");
@@ -858,21 +890,18 @@ int iris_path_tracing(const IrisScene *s, const IrisShadeParams *P, const float 
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = n_pixels * spp;
     WaveState W = wave_carve(workspace, n);
+    WaveLanes lanes = wave_lanes(W);
     CUDA_TRY(cudaMemsetAsync(L, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    CUDA_TRY(cudaMemsetAsync(W.counter, 0, WAVE_TAIL_BYTES, st));
     {
         ProfScope ps(K_WAVE_INIT, st);
-        k_wave_init_camera<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, rays, n_pixels, spp, W);
+        k_wave_init_camera<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(view_of(s), *P, *smp, rays, n_pixels, spp, W, lanes.on ? lanes.cur : nullptr, lanes.cnt);
     }
     LAUNCHED();
     if ((rc = wave_field(P, n, W.S0, W.S1, W.S2, st))) return rc;
-    if ((rc = wave_bounce_a(0, s, P, smp, 2, 0.f, n, W, st))) return rc;
-    if ((rc = wave_field(P, n, W.H0, W.M1, W.M2, st))) return rc;
-    {
-        ProfScope ps(K_WAVE_B, st);
-        k_wave_bounce_b<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W);
-    }
-    LAUNCHED();
-    if ((rc = wave_indirect(s, P, smp, n, W, indir_depth, 8, st))) return rc;
+    if ((rc = wave_bounce_a(0, s, P, smp, 2, 0.f, n, W, lanes, st))) return rc;
+    if ((rc = wave_bounce_b(0, P, n, W, lanes, st))) return rc;
+    if ((rc = wave_indirect(s, P, smp, n, W, lanes, indir_depth, 8, st))) return rc;
     {
         ProfScope ps(K_WAVE_FINISH, st);
         k_wave_finish<0><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n_pixels, spp, W, L, nullptr);
@@ -892,21 +921,18 @@ int iris_path_tracing_det(const IrisScene *s, const IrisShadeParams *P, int mode
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = n_pixels * spp;
     WaveState W = wave_carve(workspace, n);
+    WaveLanes lanes = wave_lanes(W);
     CUDA_TRY(cudaMemsetAsync(L0, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
     if (mode == 1) CUDA_TRY(cudaMemsetAsync(L1, 0, sizeof(float) * 3 * (size_t)n_pixels, st));
+    CUDA_TRY(cudaMemsetAsync(W.counter, 0, WAVE_TAIL_BYTES, st));
     {
         ProfScope ps(K_WAVE_INIT, st);
-        k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(positions, wis, 1, normals, prim, n_pixels, spp, W);
+        k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(positions, wis, 1, normals, prim, n_pixels, spp, W, lanes.on ? lanes.cur : nullptr, lanes.cnt);
     }
     LAUNCHED();
-    if ((rc = wave_bounce_a(mode == 0 ? 2 : 3, s, P, smp, 0, mode == 0 ? 0.f : roughness_level, n, W, st))) return rc;
-    if ((rc = wave_field(P, n, W.H0, W.M1, W.M2, st))) return rc;
-    {
-        ProfScope ps(K_WAVE_B, st);
-        k_wave_bounce_b<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(*P, 0.6f, 1, n, W);
-    }
-    LAUNCHED();
-    if ((rc = wave_indirect(s, P, smp, n, W, indir_depth, 2, st))) return rc;
+    if ((rc = wave_bounce_a(mode == 0 ? 2 : 3, s, P, smp, 0, mode == 0 ? 0.f : roughness_level, n, W, lanes, st))) return rc;
+    if ((rc = wave_bounce_b(2, P, n, W, lanes, st))) return rc;
+    if ((rc = wave_indirect(s, P, smp, n, W, lanes, indir_depth, 2, st))) return rc;
     {
         ProfScope ps(K_WAVE_FINISH, st);
         k_wave_finish<1><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n_pixels, spp, W, L0, mode == 1 ? L1 : nullptr);
@@ -923,13 +949,15 @@ int iris_trace_indirect(const IrisScene *s, const IrisShadeParams *P, const floa
     if (!position || !wo || !normal || !L) return fail(IRIS_ERR_INVALID, "NULL array");
     cudaStream_t st = (cudaStream_t)stream;
     WaveState W = wave_carve(workspace, n);
+    WaveLanes lanes = wave_lanes(W);
+    CUDA_TRY(cudaMemsetAsync(W.counter, 0, WAVE_TAIL_BYTES, st));
     {
         ProfScope ps(K_WAVE_INIT, st);
-        k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(position, wo, 0, normal, nullptr, n, 1, W);
+        k_wave_init_points<<<blocks_for(n), IRIS_BLOCK, 0, st>>>(position, wo, 0, normal, nullptr, n, 1, W, lanes.on ? lanes.cur : nullptr, lanes.cnt);
     }
     LAUNCHED();
     if ((rc = wave_field(P, n, W.S0, W.S1, W.S2, st))) return rc;
-    if ((rc = wave_indirect(s, P, smp, n, W, indir_depth, 0, st))) return rc;
+    if ((rc = wave_indirect(s, P, smp, n, W, lanes, indir_depth, 0, st))) return rc;
     {
         ProfScope ps(K_WAVE_FINISH, st);
         k_wave_finish<2><<<blocks_for(n), IRIS_BLOCK, 0, st>>>(n, 1, W, L, nullptr);

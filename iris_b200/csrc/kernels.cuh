@@ -286,7 +286,15 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_primary(SceneView S, IrisShadePa
 #define IRIS_QUEUE_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_QUEUE_MINBLOCKS) k_trace_queue(SceneView S, const float4 *__restrict__ ro, const float4 *__restrict__ rd, int64_t n_rays,
-                                                             int64_t n_anyhit, float4 *__restrict__ hit, unsigned long long *counter) {
+                                                             int64_t n_anyhit, float4 *__restrict__ hit, unsigned long long *counter,
+                                                             const unsigned long long *__restrict__ n_lanes_dev, int rays_per_lane) {
+    // n_lanes_dev != NULL: the queue holds rays_per_lane x (*n_lanes_dev) rays (the live lanes of a wavefront bounce, counted on the
+    // device); with two rays per lane the first half are the occlusion queries
+    if (n_lanes_dev != nullptr) {
+        const int64_t c = (int64_t)*n_lanes_dev;
+        n_rays = rays_per_lane * c;
+        n_anyhit = rays_per_lane == 2 ? c : 0;
+    }
     uint2 stack[IRIS_STACK];
     TravState T;
     T.done = true;

@@ -4,6 +4,13 @@
 // THERE (emitter.py:210-219, threshold 0.6), so the field (tensor-core MLP kernel, field.cuh) has to run between "trace" and
 // "shade": each bounce is bounce_a (NEE + BSDF sample + closest hit) -> k_field_forward on the hit points -> bounce_b
 // (emitter / SLF radiance, MIS, state update).  Lane state lives in HBM as float4 streams (208 B per lane).
+//
+// Lane compaction (the reference shrinks its lane set at every depth with boolean masks, utils/path_tracing.py:347-352,492-501):
+// the ray-queue form keeps a list of the lanes that are still alive (`idx`, `cnt` on the device; warp-aggregated appends in
+// k_wave_init_* / k_wave_bounce_b).  Per bounce, thread j of the generator / resolve / shade kernels works on lane idx[j], the ray
+// queue, the hit records and the material scratch are indexed by j (dense), the persistent trace kernel and the field kernel read
+// the live count from device memory, and blocks past the count exit at once -- no host synchronisation, no work on dead lanes.
+// Per-lane results do not depend on the order of the list (uniforms are keyed by the lane id), so outputs are unchanged bit for bit.
 #pragma once
 #include "kernels.cuh"
 
@@ -27,16 +34,23 @@ struct WaveState {
     float4 *RD;   // 2n: direction | prim_limit
     float4 *HIT;  // 2n: t u v | slot
     float4 *PN;   // n: emitter-sample contribution to add if the shadow ray is unoccluded | bsdf pdf
-    unsigned long long *counter;
+    int32_t *idxA, *idxB;         // live-lane lists (ping-pong between bounces)
+    unsigned long long *counter;  // dynamic-fetch counter of k_trace_queue
+    unsigned long long *cnt;      // cnt[k] = number of live lanes entering bounce k (WAVE_MAX_BOUNCES + 1 entries)
 };
-#define WAVE_STREAMS 22   // 14 state + 7 queue streams per lane (+ one stream's worth of slack that holds the fetch counter)
+#define WAVE_STREAMS 22          // 14 state + 7 queue streams per lane + one stream that holds the two live-lane lists
+#define WAVE_TAIL_BYTES 1024     // fetch counter + live counts, after the streams
+#define WAVE_MAX_BOUNCES 64
 __host__ __device__ inline WaveState wave_carve(void *base, int64_t n) {
     float4 *p = reinterpret_cast<float4 *>(base);
     WaveState w;
     w.S0 = p; w.S1 = p + n; w.S2 = p + 2 * n; w.S3 = p + 3 * n; w.S4 = p + 4 * n; w.S5 = p + 5 * n; w.S6 = p + 6 * n; w.S7 = p + 7 * n;
     w.S8 = p + 8 * n; w.H0 = p + 9 * n; w.H1 = p + 10 * n; w.H2 = p + 11 * n; w.M1 = p + 12 * n; w.M2 = p + 13 * n;
     w.RO = p + 14 * n; w.RD = p + 16 * n; w.HIT = p + 18 * n; w.PN = p + 20 * n;
-    w.counter = reinterpret_cast<unsigned long long *>(p + 21 * n);
+    w.idxA = reinterpret_cast<int32_t *>(p + 21 * n);
+    w.idxB = w.idxA + n;
+    w.counter = reinterpret_cast<unsigned long long *>(p + 22 * n);
+    w.cnt = w.counter + 8;
     return w;
 }
 
@@ -59,13 +73,30 @@ __device__ __forceinline__ void sample_cols6(const IrisSampler &s, int64_t lane,
 #pragma unroll
     for (int k = 0; k < 6; ++k) u[k] = v[off + k];
 }
+// warp-aggregated append of lane id `i` to a live-lane list (one atomic per warp; order inside the warp is kept)
+__device__ __forceinline__ void wave_append(int32_t i, int32_t *idx, unsigned long long *cnt) {
+    const unsigned act = __activemask(), lane = threadIdx.x & 31u;
+    const int leader = __ffs(act) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(cnt, (unsigned long long)__popc(act));
+    base = __shfl_sync(act, base, leader);
+    idx[base + __popc(act & ((1u << lane) - 1u))] = i;
+}
+// thread j of a bounce kernel -> lane id (dense list, or the identity when no list is kept); false: nothing to do
+__device__ __forceinline__ bool wave_lane(const int32_t *idx, const unsigned long long *cnt, int64_t n, int64_t &i, int64_t &c) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    c = idx ? (int64_t)*cnt : n;
+    if (j >= c) return false;
+    i = idx ? (int64_t)idx[j] : j;
+    return true;
+}
 __device__ __forceinline__ float nan0(float x) { return x != x ? 0.f : x; }
 __device__ __forceinline__ f3 nan0(f3 v) { return mk3(nan0(v.x), nan0(v.y), nan0(v.z)); }
 __device__ __forceinline__ f3 ld4(const float4 *p, int64_t i) { const float4 v = p[i]; return mk3(v.x, v.y, v.z); }
 
 // ---- init: camera rays (path_tracing :231-246)
 __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_init_camera(SceneView S, IrisShadeParams P, IrisSampler smp, const float *__restrict__ rays,
-                                                                  int64_t n_pixels, int spp, WaveState W) {
+                                                                  int64_t n_pixels, int spp, WaveState W, int32_t *idx, unsigned long long *cnt) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pixels * spp) return;
     const int64_t pix = i / spp;
@@ -89,13 +120,14 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_init_camera(SceneView S, Ir
     W.S6[i] = make_float4(Le.x, Le.y, Le.z, 0.f);
     W.S7[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     W.S8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx && code == -2) wave_append((int32_t)i, idx, cnt);
 }
 
 // ---- init: explicit surface points.  PIXELS: per-pixel arrays repeated spp times (det_*), prim == -1 disables the pixel;
 //      otherwise one lane per row (trace_indirect).
 __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_init_points(const float *__restrict__ position, const float *__restrict__ wo_or_wi, int negate_dir,
                                                                   const float *__restrict__ normal, const int32_t *__restrict__ prim, int64_t n_rows,
-                                                                  int spp, WaveState W) {
+                                                                  int spp, WaveState W, int32_t *idx, unsigned long long *cnt) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows * spp) return;
     const int64_t r = i / spp;
@@ -110,6 +142,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_init_points(const float *__
     W.S6[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     W.S7[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     W.S8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx && ok) wave_append((int32_t)i, idx, cnt);
 }
 
 // ---- bounce_a: NEE + BSDF sample + closest hit.
@@ -195,12 +228,15 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_a(SceneView S, IrisS
 // ---- the same bounce through the ray queue: k_wave_gen writes the two rays of a lane and the emitter-sample contribution that is
 // pending on the shadow ray, k_trace_queue (kernels.cuh) traces, k_wave_resolve applies the contribution and stores the next hit.
 template <int KIND>
-__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, IrisSampler smp, int col0, float level, int64_t n, WaveState W) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, IrisSampler smp, int col0, float level, int64_t n, WaveState W, const int32_t *__restrict__ idx,
+                                                          const unsigned long long *__restrict__ cnt) {
+    int64_t i, c;
+    if (!wave_lane(idx, cnt, n, i, c)) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t off = KIND <= 1 ? c : 0;             // queue layout: shadow rays [0,c), closest-hit rays [c,2c); without NEE only [0,c)
     const float4 empty = make_float4(0.f, 0.f, 0.f, -1.f);
     const float4 s0 = W.S0[i];
-    if (__float_as_int(s0.w) != -2) { W.RO[i] = empty; W.RO[n + i] = empty; return; }
+    if (__float_as_int(s0.w) != -2) { if (KIND <= 1) W.RO[j] = empty; W.RO[off + j] = empty; return; }
     const f3 x0 = mk3(s0.x, s0.y, s0.z), n0 = ld4(W.S1, i), wo = ld4(W.S3, i);
     float u[6];
     sample_cols6(smp, i, col0, u);
@@ -260,20 +296,25 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, Iris
         W.S7[i] = make_float4(w0, w0, w0, 0.f);
         W.S8[i] = make_float4(w1, w1, w1, 0.f);
     }
-    W.RO[i] = ro_s;
-    W.RD[i] = rd_s;
-    W.RO[n + i] = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
-    W.RD[n + i] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
-    W.PN[i] = make_float4(pend.x, pend.y, pend.z, bpdf);
+    if (KIND <= 1) {
+        W.RO[j] = ro_s;
+        W.RD[j] = rd_s;
+    }
+    W.RO[off + j] = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
+    W.RD[off + j] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
+    W.PN[j] = make_float4(pend.x, pend.y, pend.z, bpdf);
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_resolve(SceneView S, int64_t n, WaveState W) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (__float_as_int(W.S0[i].w) != -2) { W.H0[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); return; }
-    const float4 pn = W.PN[i];
-    if (KIND <= 1 && W.RO[i].w >= 0.f && __float_as_int(W.HIT[i].w) < 0) {      // shadow ray cast and unoccluded
+__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_resolve(SceneView S, int64_t n, WaveState W, const int32_t *__restrict__ idx,
+                                                              const unsigned long long *__restrict__ cnt) {
+    int64_t i, c;
+    if (!wave_lane(idx, cnt, n, i, c)) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t off = KIND <= 1 ? c : 0;
+    if (__float_as_int(W.S0[i].w) != -2) { W.H0[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); return; }
+    const float4 pn = W.PN[j];
+    if (KIND <= 1 && W.RO[j].w >= 0.f && __float_as_int(W.HIT[j].w) < 0) {      // shadow ray cast and unoccluded
         if (KIND == 0) {
             const f3 a = ld4(W.S6, i) + mk3(pn.x, pn.y, pn.z);
             W.S6[i] = make_float4(a.x, a.y, a.z, 0.f);
@@ -282,31 +323,34 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_resolve(SceneView S, int64_
             W.S5[i] = make_float4(a.x, a.y, a.z, 0.f);
         }
     }
-    const float4 dq = W.RD[n + i];
+    const float4 dq = W.RD[off + j];
     const f3 wi = mk3(dq.x, dq.y, dq.z);
     f3 hp, hn;
-    const Hit h = queue_hit_surface(S, W.HIT[n + i], wi, hp, hn);
-    W.H0[i] = make_float4(hp.x, hp.y, hp.z, __int_as_float(h.prim >= 0 ? -2 : -1));
-    W.H1[i] = make_float4(hn.x, hn.y, hn.z, pn.w);
-    W.H2[i] = make_float4(wi.x, wi.y, wi.z, __int_as_float(h.prim));
+    const Hit h = queue_hit_surface(S, W.HIT[off + j], wi, hp, hn);
+    W.H0[j] = make_float4(hp.x, hp.y, hp.z, __int_as_float(h.prim >= 0 ? -2 : -1));
+    W.H1[j] = make_float4(hn.x, hn.y, hn.z, pn.w);
+    W.H2[j] = make_float4(wi.x, wi.y, wi.z, __int_as_float(h.prim));
 }
 
 // ---- bounce_b: radiance at the hit (emitter, or SLF when the material THERE is rougher than tau), MIS, state update.
 // KIND as above; HAS_FIELD = false is the BaseBRDF case (roughness == 1 everywhere).
 template <int KIND>
-__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_b(IrisShadeParams P, float tau, int has_field, int64_t n, WaveState W) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_b(IrisShadeParams P, float tau, int has_field, int64_t n, WaveState W,
+                                                               const int32_t *__restrict__ idx, const unsigned long long *__restrict__ cnt,
+                                                               int32_t *__restrict__ idx_next, unsigned long long *__restrict__ cnt_next) {
+    int64_t i, c;
+    if (!wave_lane(idx, cnt, n, i, c)) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // hit records / material scratch are indexed by the list position
     const float4 s0 = W.S0[i];
     if (__float_as_int(s0.w) != -2) return;
     const f3 x0 = mk3(s0.x, s0.y, s0.z);
-    const float4 h0 = W.H0[i], h1 = W.H1[i], h2 = W.H2[i];
+    const float4 h0 = W.H0[j], h1 = W.H1[j], h2 = W.H2[j];
     const f3 pn = mk3(h0.x, h0.y, h0.z), nn = mk3(h1.x, h1.y, h1.z), wi = mk3(h2.x, h2.y, h2.z);
     const int32_t prim = __float_as_int(h2.w);
     float bpdf = h1.w;
     const bool has_mat = has_field && prim >= 0;            // the field kernel only writes M1 / M2 for lanes whose ray hit something
-    const float4 m2 = has_mat ? W.M2[i] : make_float4(0.f, 0.f, 0.f, 1.f);
-    const float m_next = has_mat ? W.M1[i].w : 0.f;
+    const float4 m2 = has_mat ? W.M2[j] : make_float4(0.f, 0.f, 0.f, 1.f);
+    const float m_next = has_mat ? W.M1[j].w : 0.f;
     // model/emitter.py:180-221
     f3 Le = mk3(0.f, 0.f, 0.f);
     float epdf = 0.f;
@@ -348,6 +392,7 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_bounce_b(IrisShadeParams P,
     W.S1[i] = make_float4(nn.x, nn.y, nn.z, m_next);
     W.S2[i] = m2;
     W.S3[i] = make_float4(-wi.x, -wi.y, -wi.z, 0.f);
+    if (idx_next && valid_next) wave_append((int32_t)i, idx_next, cnt_next);
 }
 
 // ---- finish.  MODE 0: per-pixel mean of S6 + S7*S5 (path_tracing).  MODE 1: det: out0 = mean S7*(S6+S5), out1 = mean S8*(S6+S5).

@@ -638,8 +638,9 @@ def test_wavefront_queue_equals_fused_wave_bounce(small):
     pos, nrm, wo, tri = p[v].contiguous(), n[v].contiguous(), (-rays[:, 3:6])[v].contiguous(), prim[v].contiguous()
     res = []
     try:
-        for impl in (0, 1):
+        for impl, compact in ((0, 1), (1, 1), (1, 0)):          # fused bounce | ray queue with live-lane lists (default) | ray queue over all lanes
             core.C.check(lib.iris_set_option(b"wave_impl", impl))
+            core.C.check(lib.iris_set_option(b"wave_compact", compact))
             smp = core.Sampler(seed=9)
             res.append((core.path_tracing(small["scene"], small["tables"], rays, spp, depth, smp),
                         core.path_tracing_det(small["scene"], small["tables"], 0, 0.0, pos, wo, nrm, tri, spp, depth, smp),
@@ -647,9 +648,14 @@ def test_wavefront_queue_equals_fused_wave_bounce(small):
                         core.trace_indirect(small["scene"], small["tables"], pos, wo, nrm, depth, smp)))
     finally:
         core.C.check(lib.iris_set_option(b"wave_impl", 1))
-    for a, b in zip(res[0][:-1], res[1][:-1]):
-        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
-    assert torch.equal(res[0][-1], res[1][-1])              # trace_indirect is per lane: no atomics, bit-identical
+        core.C.check(lib.iris_set_option(b"wave_compact", 1))
+    for other in (res[1], res[2]):
+        for a, b in zip(res[0][:-1], other[:-1]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+        assert torch.equal(res[0][-1], other[-1])           # trace_indirect is per lane: no atomics, bit-identical
+    # lane compaction changes which thread works on a lane, never the lane's arithmetic: the per-pixel sums see the same addends
+    for a, b in zip(res[1], res[2]):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
 
 
 def test_persistent_intersect_equals_static_intersect():
