@@ -11,6 +11,7 @@ struct f3 {
     float x, y, z;
 };
 __host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ bool is_zero3(f3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }   // false for NaN
 __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }

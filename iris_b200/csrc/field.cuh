@@ -659,11 +659,13 @@ __global__ void __launch_bounds__(FIELD_BWD_BLOCK, 512 / FIELD_BWD_BLOCK) k_fiel
 template <bool WS>
 __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams P, int64_t n, const float *__restrict__ position,
                                                                  const float4 *__restrict__ r5, FieldAct act, float *__restrict__ d_grid) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride over 256-sample blocks: the launch may cap the grid (scatter_ctas_per_sm) so that the kernel leaves room on every SM
+    // for a kernel of another stream (the next tile's ray casts are issue-bound, this kernel is bound by the reduction rate of the LSU)
     const unsigned lane = threadIdx.x & 31u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i - threadIdx.x < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float sc = i < n ? act.s[i] : 0.f;
     const bool live = sc > 0.f;
-    if (!__any_sync(0xffffffffu, live)) return;
+    if (!__any_sync(0xffffffffu, live)) continue;
     f3 p = mk3(0.f, 0.f, 0.f);
     if (live) {
         if (WS) { const float4 a = r5[i]; p = mk3(a.x, a.y, a.z); } else p = ld3(position, i);
@@ -773,6 +775,7 @@ __global__ void __launch_bounds__(256) k_field_backward_scatter(IrisShadeParams 
                 }
             }
         }
+    }
     }
 }
 

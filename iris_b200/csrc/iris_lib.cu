@@ -87,6 +87,7 @@ static int g_bake_impl = 2;        // 2: persistent warps with the generator / r
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
 static int g_wave_compact = 1;     // 1: live-lane lists (dense queues, dead lanes cost nothing), 0: every kernel over all lanes (A/B)
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
+static int g_scatter_ctas = 0;     // > 0: cap the grid of the grid-gradient scatter at this many CTAs per SM (it strides over the samples)
 static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
 static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
 static bool g_field_ready[64] = {false};
@@ -257,6 +258,7 @@ int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
     if (name && std::strcmp(name, "persist_ctas_per_sm") == 0 && value >= 1 && value <= 16) { g_persist_ctas = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "scatter_ctas_per_sm") == 0 && value >= 0 && value <= 8) { g_scatter_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "tc5_ctas_per_sm") == 0 && value >= 1 && value <= 8) { g_tc5_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "field_smem_carveout_pct") == 0 && value >= 0 && value <= 100) {
         // how much of the SM's 228 KB the field kernels ask to be shared memory: the rest is L1, which the hash-grid gathers live on
@@ -626,7 +628,8 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
         LAUNCHED();
         {
             ProfScope ps(K_FIELD_SCATTER, st);
-            const unsigned gs = (unsigned)((m + 255) / 256);
+            unsigned gs = (unsigned)((m + 255) / 256);
+            if (g_scatter_ctas > 0) gs = std::min<unsigned>(gs, (unsigned)(g_scatter_ctas * (g_sm_count > 0 ? g_sm_count : 148)));
             if (r5) k_field_backward_scatter<true><<<gs, 256, 0, st>>>(*P, m, nullptr, r5 + c0, act, d_params + 9216);
             else k_field_backward_scatter<false><<<gs, 256, 0, st>>>(*P, m, position + 3 * c0, nullptr, act, d_params + 9216);
         }

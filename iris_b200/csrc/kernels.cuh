@@ -454,6 +454,14 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
                 e_nee = e;
                 if (REC >= 1) c_nee = f * s;
                 if (REC == 2) { JaN = J.da * W; JrN = J.dr * W; JmN = J.dm * W; }
+#ifndef IRIS_NO_RAY_SKIP
+                // an emitter below the horizon of x0 (NoL clamps to 0): the contribution, its coefficient and its Jacobian are all exactly
+                // zero whatever the shadow ray returns -> no shadow ray (a NaN anywhere fails the test and keeps the ray)
+                bool dead = is_zero3(L_nee);
+                if (REC >= 1) dead = dead && is_zero3(c_nee);
+                if (REC == 2) dead = dead && is_zero3(JaN) && is_zero3(JrN) && is_zero3(JmN);
+                if (dead) { ro_s = make_float4(0.f, 0.f, 0.f, -1.f); rd_s = ro_s; e_nee = -1; }
+#endif
             }
         }
         f3 wi, wb;
@@ -462,6 +470,14 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_single_gen(IrisShadeParams P, Ir
         sample_brdf<REC == 2>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
         ro_b = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
         rd_b = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
+#ifndef IRIS_NO_RAY_SKIP
+        {   // a BSDF sample with zero weight (direction below the horizon, or pdf == 0) and zero Jacobian adds nothing to L or to any
+            // gradient whatever it hits -> no ray; k_single_shade sees a miss (Le = 0) for it
+            bool dead = is_zero3(wb);
+            if (REC == 2) dead = dead && is_zero3(J.da) && is_zero3(J.dr) && is_zero3(J.dm);
+            if (dead) ro_b = make_float4(0.f, 0.f, 0.f, -1.f);
+        }
+#endif
         st[j] = make_float4(L_nee.x, L_nee.y, L_nee.z, pdf_b);
         st[nc + j] = make_float4(wb.x, wb.y, wb.z, __int_as_float(e_nee));
         if (REC >= 1) st[2 * nc + j] = make_float4(c_nee.x, c_nee.y, c_nee.z, JaN.x);
@@ -609,9 +625,13 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
                     const f3 W = emitter_radiance(P, e) * s;
                     L = L + f * W;
                     if (RECORD) {
-                        e_nee = e;
-                        c_nee = f * s;
-                        Ja = Ja + J.da * W; Jr = Jr + J.dr * W; Jm = Jm + J.dm * W;
+                        const f3 cn = f * s, ja = J.da * W, jr = J.dr * W, jm = J.dm * W;
+                        bool dead = false;
+#ifndef IRIS_NO_RAY_SKIP
+                        dead = is_zero3(f * W) && is_zero3(cn) && is_zero3(ja) && is_zero3(jr) && is_zero3(jm);   // k_single_gen drops such samples
+#endif
+                        if (!dead) { e_nee = e; c_nee = cn; }
+                        Ja = Ja + ja; Jr = Jr + jr; Jm = Jm + jm;
                     }
                 }
             }
@@ -622,7 +642,14 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_BOUNCE_MINBLOCKS) k_bounce_si
                 BrdfJac J;
                 sample_brdf<RECORD>(ub.y, ub.z, ub.w, wo, n0, mat, wi, pdf_b, wb, &J);
                 const f3 org = ray_origin(x0, wi);
-                const Hit h = trace_closest_shared(S, org, wi);
+                bool dead = false;
+#ifndef IRIS_NO_RAY_SKIP
+                dead = is_zero3(wb);                                   // zero weight (and Jacobian): no ray, as in k_single_gen
+                if (RECORD) dead = dead && is_zero3(J.da) && is_zero3(J.dr) && is_zero3(J.dm);
+#endif
+                Hit h;
+                h.t = __int_as_float(0x7f800000); h.u = h.v = 0.f; h.prim = -1; h.slot = -1;
+                if (!dead) h = trace_closest_shared(S, org, wi);
                 f3 hp, hn;
                 hit_surface(S, h, wi, hp, hn);
                 int32_t eh;
