@@ -15,7 +15,7 @@ lookups, MIS, adjoint replay).
 Prints ONE JSON line (rank 0).  `value` times the steps with inputs resident in HBM; `e2e` times the same steps through the
 public API with the rays in pinned HOST memory (H2D inside the timed region, loss + gradient read back).  The default (c3) line
 also carries `extra`: short device-timed runs (1 warm-up + 2 steps) of the other BASELINE configurations -- c4, c2, the per-GPU
-shard of c5 (8 views of the 5M-triangle room at 1920x1440, spp 128), path_tracing with 5 indirect bounces, and the per-call latency
+shard of c5 (8 views of the 5M-triangle room at 1920x1440, spp 128), the c3 step on a scan-like irregular mesh, path_tracing with 5 indirect bounces, and the per-call latency
 at the trainers' real batch shape (8192 pixels x spp 32, eager and CUDA graph) -- so that they are measured by whoever runs this file.
 `--workload c5` is the full strong-scaling configuration (64 views dealt to the ranks).
 """
@@ -256,9 +256,9 @@ class Ctx:
         """(procedural scene, device Scene, stats, tables) -- built once per triangle count."""
         import torch
         from iris_b200 import core, scenes
-        key = "c1" if w.get("cornell") else w["tris"]
+        key = "c1" if w.get("cornell") else (w["tris"], bool(w.get("irregular")))
         if key not in self.scenes:
-            sc = scenes.cornell() if w.get("cornell") else scenes.room(w["tris"], w["emitters"], seed=0)
+            sc = scenes.cornell() if w.get("cornell") else scenes.room(w["tris"], w["emitters"], seed=0, irregular=bool(w.get("irregular")))
             scene = core.Scene(sc.vertices, sc.faces, self.local)
             tables = core.ShadingTables.from_dicts(self.dev, sc.emitter_dict(), sc.slf_dict(256), bench_params(), sc.voxel_bounds())
             self.scenes[key] = (sc, scene, scene.stats(), tables)
@@ -662,6 +662,15 @@ def main():
             extra["path_tracing"] = run_path_tracing(ctx, dict(WORKLOADS["c3"]), 2, 1)
             if rank == 0:
                 extra["latency"] = run_latency(ctx, dict(WORKLOADS["c3"]), 50)
+            ctx.drop_scenes()
+            ws_ = dict(WORKLOADS["c3"])
+            ws_["irregular"], ws_["views"] = True, 2       # the c3 step on a scan-like tessellation of the same room (scenes.room(irregular=True))
+            x = run_estimator(ctx, a, ws_, 2, 1, False, True, a.tile)
+            kq = x["prof"].get("k_trace_queue")
+            extra["c3_scan_mesh"] = dict(metric="path_samples_per_sec_fwd_bwd", value=x["value"], unit="samples/s", ms_per_step=x["ms"] / 2, triangles=x["triangles"],
+                                         config="c3 step (2 views/GPU) on the irregular 1M-triangle room: cell sizes varying ~10x, jittered vertices, random diagonals, per-vertex noise, shuffled face order",
+                                         trace_queue_rays_per_s=(2 * x["n_samples_rank"] * 2 / (kq["total_ms"] * 1e-3) if kq else None),
+                                         bvh_nodes=x["stats"]["n_nodes"], bvh_depth=x["stats"]["max_depth"], bvh_build_ms=x["stats"]["build_ms"])
             ctx.drop_scenes()
             w5 = dict(WORKLOADS["c5"])
             w5["views"], w5["strong"] = 8, False             # the per-GPU shard of the 64-view sweep at N = 8: 8 views of the 5M-triangle room per GPU

@@ -25,15 +25,36 @@ import numpy as np
 
 
 # ----------------------------------------------------------------------------- mesh pieces
+def _warp01(n, rng):
+    """n+1 increasing knots on [0,1] whose spacing varies smoothly by ~10x (scan meshes are dense where the scanner was close)."""
+    x = np.linspace(0.0, 1.0, n + 1)
+    dens = np.ones_like(x)
+    for _ in range(3):
+        dens += rng.uniform(0.6, 1.6) * np.exp(-0.5 * ((x - rng.uniform(0, 1)) / rng.uniform(0.05, 0.2)) ** 2)
+    w = 1.0 / dens
+    k = np.concatenate([[0.0], np.cumsum(0.5 * (w[1:] + w[:-1]))])
+    return k / k[-1]
+
+
 def _grid_quad(p0, du, dv, nu, nv, disp=None, rng=None):
     """Tessellate the parallelogram p0 + s*du + t*dv into nu x nv cells (2 triangles each).
 
     disp: optional callable (s,t)->offset along the quad normal (displaced walls).
+    rng:  irregular ("scan-like") tessellation -- smoothly varying cell sizes, interior vertices jittered inside their cells,
+          a random diagonal per cell.  The boundary vertices stay on the boundary, so neighbouring patches still meet.
     Returns (verts (n,3) f64, faces (m,3) i64).
     """
-    s = np.linspace(0.0, 1.0, nu + 1)
-    t = np.linspace(0.0, 1.0, nv + 1)
+    if rng is not None:
+        s, t = _warp01(nu, rng), _warp01(nv, rng)
+    else:
+        s = np.linspace(0.0, 1.0, nu + 1)
+        t = np.linspace(0.0, 1.0, nv + 1)
     S, T = np.meshgrid(s, t, indexing="ij")
+    if rng is not None and nu > 1 and nv > 1:
+        ds = np.minimum(np.diff(s)[:-1], np.diff(s)[1:])[:, None]
+        dt = np.minimum(np.diff(t)[:-1], np.diff(t)[1:])[None, :]
+        S[1:-1, 1:-1] += rng.uniform(-0.4, 0.4, size=(nu - 1, nv - 1)) * ds
+        T[1:-1, 1:-1] += rng.uniform(-0.4, 0.4, size=(nu - 1, nv - 1)) * dt
     P = p0[None, None, :] + S[..., None] * du[None, None, :] + T[..., None] * dv[None, None, :]
     if disp is not None:
         n = np.cross(du, dv)
@@ -45,11 +66,16 @@ def _grid_quad(p0, du, dv, nu, nv, disp=None, rng=None):
     b = idx[1:, :-1].ravel()
     c = idx[1:, 1:].ravel()
     d = idx[:-1, 1:].ravel()
+    if rng is not None:
+        flip = rng.random(len(a)) < 0.5                             # the other diagonal: (a,b,d) + (b,c,d), same orientation
+        f1 = np.where(flip[:, None], np.stack([a, b, d], 1), np.stack([a, b, c], 1))
+        f2 = np.where(flip[:, None], np.stack([b, c, d], 1), np.stack([a, c, d], 1))
+        return verts, np.concatenate([f1, f2], 0)
     faces = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], 0)
     return verts, faces
 
 
-def _box(center, half, rot_y, n):
+def _box(center, half, rot_y, n, rng=None):
     """Axis box rotated about y, each face an n x n grid."""
     cx = np.asarray(center, np.float64)
     hx, hy, hz = half
@@ -65,7 +91,7 @@ def _box(center, half, rot_y, n):
         (cx - ex - ey - ez, 2 * ex, 2 * ey),  # -z
         (cx - ex - ey + ez, 2 * ey, 2 * ex),  # +z
     ):
-        parts.append(_grid_quad(o, u, v, n, n))
+        parts.append(_grid_quad(o, u, v, n, n, None, rng))
     return parts
 
 
@@ -210,7 +236,7 @@ def surface_voxels(vertices, faces, vmin, vmax, H, chunk=1 << 20):
 
 
 def make_room(n_tris=10_000, n_emitters=2, seed=0, half=(1.0, 1.0, 1.0), displaced=False,
-              furniture=2, name="cornell"):
+              furniture=2, name="cornell", irregular=False):
     """Closed room with tessellated walls, `furniture` primitives and ceiling light quads.
 
     n_tris is a target; the exact count is whatever the tessellation yields (reported in .n_tris).
@@ -224,19 +250,24 @@ def make_room(n_tris=10_000, n_emitters=2, seed=0, half=(1.0, 1.0, 1.0), displac
     n_wall = max(1, int(round(math.sqrt(n_tris * wall_frac / 12.0))))
     amp = 0.004 * min(half) if displaced else 0.0
 
+    irr = np.random.default_rng(seed + 4242) if irregular else None      # irregular: scan-like tessellation (see _grid_quad)
+
     def disp_fn(ph):
         if not displaced:
             return None
+        if irregular:      # scanner noise on top of the smooth displacement: per-vertex, ~1/4 of the smooth amplitude
+            return lambda S, T: amp * (np.sin(37.0 * S + ph) * np.cos(29.0 * T + 2 * ph) + 0.5 * np.sin(91.0 * S * T + ph)
+                                       + 0.25 * irr.standard_normal(S.shape) * (np.minimum(np.minimum(S, 1 - S), np.minimum(T, 1 - T)) > 0))
         return lambda S, T: amp * (np.sin(37.0 * S + ph) * np.cos(29.0 * T + 2 * ph) + 0.5 * np.sin(91.0 * S * T + ph))
 
     c = np.array
     parts = [
-        _grid_quad(c([-hx, -hy, -hz]), c([2 * hx, 0, 0]), c([0, 0, 2 * hz]), n_wall, n_wall, disp_fn(0.1)),   # floor
-        _grid_quad(c([-hx, hy, -hz]), c([0, 0, 2 * hz]), c([2 * hx, 0, 0]), n_wall, n_wall, disp_fn(0.7)),    # ceiling
-        _grid_quad(c([-hx, -hy, -hz]), c([0, 2 * hy, 0]), c([2 * hx, 0, 0]), n_wall, n_wall, disp_fn(1.3)),   # back  (-z)
-        _grid_quad(c([-hx, -hy, hz]), c([2 * hx, 0, 0]), c([0, 2 * hy, 0]), n_wall, n_wall, disp_fn(1.9)),    # front (+z)
-        _grid_quad(c([-hx, -hy, -hz]), c([0, 0, 2 * hz]), c([0, 2 * hy, 0]), n_wall, n_wall, disp_fn(2.5)),   # left  (-x)
-        _grid_quad(c([hx, -hy, -hz]), c([0, 2 * hy, 0]), c([0, 0, 2 * hz]), n_wall, n_wall, disp_fn(3.1)),    # right (+x)
+        _grid_quad(c([-hx, -hy, -hz]), c([2 * hx, 0, 0]), c([0, 0, 2 * hz]), n_wall, n_wall, disp_fn(0.1), irr),   # floor
+        _grid_quad(c([-hx, hy, -hz]), c([0, 0, 2 * hz]), c([2 * hx, 0, 0]), n_wall, n_wall, disp_fn(0.7), irr),    # ceiling
+        _grid_quad(c([-hx, -hy, -hz]), c([0, 2 * hy, 0]), c([2 * hx, 0, 0]), n_wall, n_wall, disp_fn(1.3), irr),   # back  (-z)
+        _grid_quad(c([-hx, -hy, hz]), c([2 * hx, 0, 0]), c([0, 2 * hy, 0]), n_wall, n_wall, disp_fn(1.9), irr),    # front (+z)
+        _grid_quad(c([-hx, -hy, -hz]), c([0, 0, 2 * hz]), c([0, 2 * hy, 0]), n_wall, n_wall, disp_fn(2.5), irr),   # left  (-x)
+        _grid_quad(c([hx, -hy, -hz]), c([0, 2 * hy, 0]), c([0, 0, 2 * hz]), n_wall, n_wall, disp_fn(3.1), irr),    # right (+x)
     ]
     n_so_far = sum(len(f) for _, f in parts)
     if furniture:
@@ -249,7 +280,7 @@ def make_room(n_tris=10_000, n_emitters=2, seed=0, half=(1.0, 1.0, 1.0), displac
                 hw = rng.uniform(0.12, 0.3) * min(hx, hz)
                 hh = rng.uniform(0.2, 0.6) * hy
                 n = max(1, int(round(math.sqrt(per / 12.0))))
-                parts += _box((px, -hy + hh + 1e-3 * hy, pz), (hw, hh, hw), rng.uniform(0, math.pi), n)
+                parts += _box((px, -hy + hh + 1e-3 * hy, pz), (hw, hh, hw), rng.uniform(0, math.pi), n, irr)
             else:
                 r = rng.uniform(0.12, 0.25) * min(half)
                 n = max(3, int(round(math.sqrt(per / 4.0))))
@@ -272,6 +303,9 @@ def make_room(n_tris=10_000, n_emitters=2, seed=0, half=(1.0, 1.0, 1.0), displac
     V, F = _merge(parts)
     is_emitter = np.zeros(len(F), bool)
     is_emitter[n_geom:] = True
+    if irregular:          # a scan has no spatial face order: shuffle the faces (prim index == face order, so is_emitter moves along)
+        perm = irr.permutation(len(F))
+        F, is_emitter = F[perm], is_emitter[perm]
     K = int(is_emitter.sum())
     rad = np.zeros((len(F), 3), np.float32)
     rad[:K] = rng.uniform(5.0, 15.0, size=(K, 3)).astype(np.float32)      # C4: radiance U(5,15)
@@ -283,8 +317,10 @@ def cornell(seed=0):
     return make_room(10_000, 2, seed, (1.0, 1.0, 1.0), displaced=False, furniture=2, name="cornell-10k")
 
 
-def room(n_tris=1_000_000, n_emitters=16, seed=0):
-    """C2-C5: furnished room with displaced walls (half extents 3 x 1.4 x 2.5 m)."""
+def room(n_tris=1_000_000, n_emitters=16, seed=0, irregular=False):
+    """C2-C5: furnished room with displaced walls (half extents 3 x 1.4 x 2.5 m).  irregular=True: the same room with a scan-like
+    tessellation (cell sizes varying ~10x, jittered vertices, random diagonals, per-vertex noise, shuffled face order) -- the
+    reference's real inputs are ScanNet++ reconstructions, not regular grids."""
     nf = 12 if n_tris >= 100_000 else 4
     return make_room(n_tris, n_emitters, seed, (3.0, 1.4, 2.5), displaced=True, furniture=nf,
-                     name="room-%dk" % (n_tris // 1000))
+                     name="%sroom-%dk" % ("scan-" if irregular else "", n_tris // 1000), irregular=irregular)

@@ -107,6 +107,20 @@ def test_intersect_bit_exact_room_200k(builder):
     _check_intersect(scene, osc, o, d, dev)
 
 
+@pytest.mark.parametrize("builder", [0, 1])
+def test_intersect_bit_exact_scan_like_room(builder):
+    """The same room with an irregular, scan-like tessellation (cell sizes varying ~10x, jittered vertices, random diagonals,
+    per-vertex noise, shuffled face order -- scenes.room(irregular=True)): hits still bit-exact against the oracle, both builders."""
+    dev = _gpu()
+    from iris_b200 import core, scenes
+    from oracle.intersect import OracleScene
+    sc = scenes.room(200_000, 16, seed=5, irregular=True)
+    osc = OracleScene(sc.vertices, sc.faces)
+    scene = core.Scene(sc.vertices, sc.faces, 0, builder=builder)
+    o, d = _rays_for_parity(sc, osc, 200_000, 4)
+    _check_intersect(scene, osc, o, d, dev)
+
+
 def test_intersect_edge_cases():
     dev = _gpu()
     from iris_b200 import core

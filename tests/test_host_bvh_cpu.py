@@ -40,11 +40,12 @@ def _host_trace(L, sc, o, d):
     return out, info
 
 
-@pytest.mark.parametrize("which", ["cornell", "room60k"])
+@pytest.mark.parametrize("which", ["cornell", "room60k", "scanroom60k"])
 def test_bvh8_traversal_matches_oracle(host_lib, which):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_gpu_parity import _rays_for_parity
-    sc = scenes.cornell() if which == "cornell" else scenes.room(60_000, 16, seed=3)
+    # scanroom: the irregular, scan-like tessellation (varying cell sizes, jittered vertices, random diagonals, shuffled faces)
+    sc = scenes.cornell() if which == "cornell" else scenes.room(60_000, 16, seed=3, irregular=(which == "scanroom60k"))
     osc = OracleScene(sc.vertices, sc.faces)
     o, d = _rays_for_parity(sc, osc, 40_000, 1)
     o, d = np.ascontiguousarray(o), np.ascontiguousarray(d)
