@@ -41,7 +41,7 @@ const char *iris_last_error(void);
 const char *iris_version(void);
 /* Binding handshake: what = 0 -> IRIS_ABI_VERSION, 1 -> sizeof(IrisShadeParams), 2 -> sizeof(IrisSampler), 3 -> sizeof(IrisSceneStats),
  * anything else -> -1.  A binding that mirrors the structs by hand (ctypes, cgo) compares these before the first call. */
-#define IRIS_ABI_VERSION 2
+#define IRIS_ABI_VERSION 3
 int64_t iris_abi_info(int what);
 
 /* ------------------------------------------------------------------------------------------------
@@ -262,6 +262,20 @@ int iris_crf_forward(const float *hdr, const float *exposure, int32_t exposure_s
                      float *ldr, void *stream);
 int iris_crf_backward(const float *hdr, const float *exposure, int32_t exposure_stride, const float *crf, int32_t n_bins,
                       const float *d_ldr, int64_t n, float *d_hdr, float *d_crf, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Shading-map denoiser -- the post-process bake_shading.py:81,126-131,190-203 applies to every baked map before writing it
+ * (`denoiser = mitsuba.OptixDenoiser(img_hw[::-1]); Ld = denoiser(Ld)`).  OptiX's denoiser is a learned network inside an absent
+ * third-party library: parity with it is unpinned by nature.  This entry is a deterministic edge-avoiding a-trous wavelet filter
+ * (Dammertz et al. 2010; definition in csrc/denoise.cuh, numpy restatement in oracle/denoise.py) over an (height, width, 3) map:
+ * `iterations` levels (tap spacing 1, 2, 4, ...), colour edge-stopping sigma_c (halved per level), and -- when the optional guide
+ * images are given -- normal (cosine^sigma_n) and position (sigma_x, scene units) edge-stopping from the bake's primary hits.
+ * Pixels whose guide normal is (0,0,0) (no primary hit) pass through and are never used as taps.  normal / position may be NULL.
+ * `out` must not alias `image`; workspace (iris_denoise_workspace_bytes) is needed for iterations > 1.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t iris_denoise_workspace_bytes(int32_t height, int32_t width);
+int iris_denoise_atrous(const float *image, const float *normal, const float *position, int32_t height, int32_t width, int32_t iterations,
+                        float sigma_c, float sigma_n, float sigma_x, float *out, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t iris_launch_count(void);

@@ -68,6 +68,8 @@ PROTOTYPES = {
     "iris_emitter_geometry": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "iris_brdf_shading_forward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "iris_brdf_shading_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
+    "iris_denoise_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "iris_denoise_atrous": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_i64, c_vp]),
     "iris_crf_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "iris_crf_backward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "iris_bsdf_sample": (ctypes.c_int, [ctypes.c_int, c_vp, c_i32, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -80,7 +82,7 @@ PROTOTYPES = {
 }
 
 _LIB = None
-ABI_VERSION = 2          # include/iris_b200.h: IRIS_ABI_VERSION
+ABI_VERSION = 3          # include/iris_b200.h: IRIS_ABI_VERSION
 
 
 def lib():

@@ -1,6 +1,6 @@
 """Stand-in for the parts of `mitsuba` the reference's drivers touch: `set_variant`, `load_dict` for a
 single-mesh scene (train_emitter.py:57-63), `math.RayEpsilon` (bake_shading.py:117), `OptixDenoiser(wh)(img)`
-(bake_shading.py:81,129 -- pass-through: parity is defined before the denoiser), `TensorXf` (refine_shading.py:124).
+(bake_shading.py:81,129 -- the library's a-trous filter; parity is defined before the denoiser), `TensorXf` (refine_shading.py:124).
 `load_dict` parses the OBJ / PLY mesh and builds the BVH scene the kernels traverse."""
 from __future__ import annotations
 
@@ -40,13 +40,28 @@ def TensorXf(a):
 
 
 class OptixDenoiser:
-    """Pass-through (the OptiX AI denoiser is a post-process outside the hot path; shading-map parity is defined pre-denoise)."""
+    """`denoiser = mitsuba.OptixDenoiser(img_hw[::-1]); Ld = denoiser(Ld).numpy()` (bake_shading.py:81,129,198-199).
 
-    def __init__(self, input_size, albedo=False, normals=False, temporal=False):
+    OptiX's denoiser is a learned network (absent, no weights): parity with it cannot be defined, and shading-map parity is defined
+    pre-denoise.  With a GPU this runs the library's own a-trous filter (iris_b200.denoise.atrous, csrc/denoise.cuh) on the map;
+    `normal=` / `position=` (H,W,3 guides from the bake's primary hits) sharpen its edge stopping when the caller has them.
+    `passthrough=True` (or no CUDA device) returns the input unchanged."""
+
+    def __init__(self, input_size, albedo=False, normals=False, temporal=False, passthrough=False, **filter_args):
         self.input_size = tuple(input_size)
+        self.passthrough = bool(passthrough)
+        self.filter_args = filter_args
 
-    def __call__(self, img, *a, **k):
-        return img if isinstance(img, _Array) else _Array(img)
+    def __call__(self, img, *a, normal=None, position=None, **k):
+        arr = img.numpy() if isinstance(img, _Array) else np.asarray(img)
+        import torch
+        if self.passthrough or not torch.cuda.is_available() or arr.ndim != 3 or arr.shape[-1] != 3:
+            return _Array(arr)
+        from .. import denoise
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = lambda x: None if x is None else torch.as_tensor(np.asarray(x, np.float32)).to(dev)
+        out = denoise.atrous(torch.as_tensor(np.ascontiguousarray(arr, np.float32)).to(dev), g(normal), g(position), **self.filter_args)
+        return _Array(out.cpu().numpy())
 
 
 def read_obj(path):

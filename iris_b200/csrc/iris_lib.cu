@@ -20,6 +20,7 @@
 #include "slf_bake.cuh"
 #include "emitter_extract.cuh"
 #include "bsdf_api.cuh"
+#include "denoise.cuh"
 
 struct IrisScene {
     int device = 0;
@@ -1118,6 +1119,36 @@ int iris_brdf_shading_backward(const float *mat, const float *diffuse, const flo
     if (!mat || !diffuse || !specular0 || !specular1 || !dL || !d_mat) return fail(IRIS_ERR_INVALID, "NULL array");
     k_brdf_shading_backward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mat, diffuse, specular0, specular1, n_levels, n, dL, d_mat);
     LAUNCHED();
+    return IRIS_OK;
+}
+
+int64_t iris_denoise_workspace_bytes(int32_t height, int32_t width) { return (int64_t)std::max(height, 0) * std::max(width, 0) * 3 * (int64_t)sizeof(float); }
+
+int iris_denoise_atrous(const float *image, const float *normal, const float *position, int32_t height, int32_t width, int32_t iterations,
+                        float sigma_c, float sigma_n, float sigma_x, float *out, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (height < 0 || width < 0 || iterations < 0 || iterations > 12 || !(sigma_c > 0.f) || !(sigma_n >= 0.f) || !(sigma_x > 0.f))
+        return fail(IRIS_ERR_INVALID, "bad denoise arguments");
+    const int64_t n = (int64_t)height * width;
+    if (n == 0) return IRIS_OK;
+    if (!image || !out) return fail(IRIS_ERR_INVALID, "NULL array");
+    if (image == out) return fail(IRIS_ERR_INVALID, "denoise: out must not alias image");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iterations == 0) {
+        CUDA_TRY(cudaMemcpyAsync(out, image, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, st));
+        return IRIS_OK;
+    }
+    if (iterations > 1 && (!workspace || workspace_bytes < iris_denoise_workspace_bytes(height, width))) return fail(IRIS_ERR_WORKSPACE, "denoise: workspace too small");
+    const dim3 grid((unsigned)((width + 31) / 32), (unsigned)((height + 7) / 8));
+    float *tmp = reinterpret_cast<float *>(workspace);
+    const float *src = image;
+    for (int i = 0; i < iterations; ++i) {
+        // ping-pong so that the LAST level lands in `out`
+        float *dst = ((iterations - 1 - i) & 1) ? tmp : out;
+        const float sc = sigma_c * ldexpf(1.0f, -i);
+        k_denoise_atrous<<<grid, 256, 0, st>>>(src, normal, position, height, width, 1 << i, 1.0f / (sc * sc), sigma_n, 1.0f / (sigma_x * sigma_x), dst);
+        LAUNCHED();
+        src = dst;
+    }
     return IRIS_OK;
 }
 
