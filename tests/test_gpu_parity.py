@@ -1000,6 +1000,38 @@ def test_emitter_extraction_matches_reference_golden():
 
 
 @pytest.mark.gpu
+def test_denoise_atrous_matches_oracle():
+    """iris_denoise_atrous (the filter behind compat.mitsuba.OptixDenoiser, bake_shading.py:81,129) against its numpy restatement:
+    colour-only and guided (normals + positions from primary hits, a few no-hit pixels), odd sizes, every iteration count's
+    ping-pong parity; the compat class returns the filtered map."""
+    dev = _gpu()
+    from iris_b200 import denoise
+    from iris_b200.compat import mitsuba as cm
+    from oracle import denoise as OD
+    rng = np.random.default_rng(4)
+    H, W = 67, 93
+    img = (rng.random((H, W, 3)) * 2.0).astype(np.float32)
+    img[:, : W // 3] *= 0.2
+    nrm = rng.standard_normal((H, W, 3)).astype(np.float32) * 0.1 + np.array([0, 0, 1], np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    nrm[:, W // 2:] = np.array([0, 1, 0], np.float32)
+    nrm[10:13, 20:25] = 0.0
+    pos = np.stack(list(np.meshgrid(np.linspace(0, 3, W), np.linspace(0, 2, H), indexing="xy")) + [np.zeros((H, W))], -1).astype(np.float32)
+    for iters in (1, 2, 5):
+        for guides in (False, True):
+            kw = dict(iterations=iters, sigma_c=0.8, sigma_n=16.0, sigma_x=0.4)
+            want = OD.atrous(img, nrm if guides else None, pos if guides else None, **kw)
+            got = denoise.atrous(torch.as_tensor(img).to(dev), torch.as_tensor(nrm).to(dev) if guides else None,
+                                 torch.as_tensor(pos).to(dev) if guides else None, **kw).cpu().numpy()
+            assert np.allclose(got, want, rtol=2e-4, atol=2e-6), (iters, guides, np.abs(got - want).max())
+            if guides:
+                assert np.array_equal(got[10:13, 20:25], img[10:13, 20:25])
+    out = cm.OptixDenoiser((W, H), sigma_c=0.8)(img).numpy()
+    assert out.shape == img.shape and np.allclose(out, OD.atrous(img, iterations=5, sigma_c=0.8), rtol=2e-4, atol=2e-6)
+    assert np.array_equal(cm.OptixDenoiser((W, H), passthrough=True)(img).numpy(), img)
+    assert denoise.atrous(torch.zeros(0, 5, 3, device=dev)).shape == (0, 5, 3)
+
+
 def test_c_abi_error_convention(small):
     """Bad calls return a negative status and leave a message in iris_last_error(); they never launch work (include/iris_b200.h)."""
     import ctypes

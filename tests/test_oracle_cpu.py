@@ -287,3 +287,32 @@ def test_emitter_extract_oracle_matches_reference_golden():
     assert np.array_equal(out["emitter_vertices"].numpy(), g["emitter_vertices"]) and np.array_equal(out["emitter_area"].numpy(), g["emitter_area"])
     assert np.array_equal(out["emitter_normal"].numpy(), g["emitter_normal"])
     assert tuple(out["emitter_radiance"].shape) == tuple(g["emitter_radiance_shape"])
+
+
+def test_denoise_oracle_properties():
+    """The a-trous shading-map filter (oracle/denoise.py restates csrc/denoise.cuh; OptiX parity is unpinned by nature): constant
+    images are fixed points, weights are normalised (range preserved), noise variance drops, a normal discontinuity is not crossed,
+    and pixels without a primary hit (zero normal) pass through and do not leak into their neighbours."""
+    from oracle import denoise as OD
+    rng = np.random.default_rng(0)
+    H, W = 40, 48
+    const = np.full((H, W, 3), 0.7, np.float32)
+    assert np.allclose(OD.atrous(const, iterations=4, sigma_c=0.5), const, atol=1e-6)
+    noisy = (0.5 + 0.1 * rng.standard_normal((H, W, 3))).astype(np.float32)
+    out = OD.atrous(noisy, iterations=4, sigma_c=1.0)
+    assert out.min() >= noisy.min() - 1e-6 and out.max() <= noisy.max() + 1e-6
+    assert out[8:-8, 8:-8].var() < 0.05 * noisy[8:-8, 8:-8].var()
+    # two half-planes with different normals and different radiance: the edge survives when the normal guide is given
+    img = np.where(np.arange(W)[None, :, None] < W // 2, 0.2, 0.8).astype(np.float32) * np.ones((H, W, 3), np.float32)
+    img += (0.02 * rng.standard_normal(img.shape)).astype(np.float32)
+    nrm = np.zeros((H, W, 3), np.float32)
+    nrm[:, :W // 2, 0] = 1.0
+    nrm[:, W // 2:, 1] = 1.0
+    guided = OD.atrous(img, normal=nrm, iterations=4, sigma_c=10.0)
+    plain = OD.atrous(img, iterations=4, sigma_c=10.0)
+    assert abs(guided[:, W // 2 - 1].mean() - 0.2) < 0.01 and abs(guided[:, W // 2].mean() - 0.8) < 0.01
+    assert abs(plain[:, W // 2 - 1].mean() - 0.2) > 0.1                       # without the guide the wide colour sigma blurs the edge
+    nrm[5:9, 5:9] = 0.0
+    img[5:9, 5:9] = 100.0
+    g2 = OD.atrous(img, normal=nrm, iterations=3, sigma_c=1e3)
+    assert np.array_equal(g2[5:9, 5:9], img[5:9, 5:9]) and g2[4, 4].max() < 1.0
