@@ -67,7 +67,27 @@ def both():
     torch.cuda.current_stream().wait_stream(sB)
 
 
+def bwd_two_streams():
+    """The adjoint chunks alternate between two streams (own workspaces): the latency-bound tcgen05 kernel of one chunk can sit next
+    to the reduction-bound grid scatter of the other."""
+    ev = torch.cuda.Event()
+    ev.record()
+    for k, r in enumerate(recsA):
+        st, ws = (sF, wsF) if k % 2 == 0 else (sB, wsB)
+        with torch.cuda.stream(st):
+            if k < 2:
+                st.wait_event(ev)
+            core.single_backward(tables, dL, spp, r, True, dp, workspace=ws)
+    torch.cuda.current_stream().wait_stream(sF)
+    torch.cuda.current_stream().wait_stream(sB)
+
+
 print("tile %d px x spp %d x %d chunks" % (tile, spp, n_chunks))
+t1 = timed(lambda: bwd(recsA, wsB))
+t2 = timed(bwd_two_streams)
+print("adjoint of %d chunks: one stream %.2f ms, two streams %.2f ms (%.3f)" % (n_chunks, t1, t2, t2 / t1))
+if len(sys.argv) > 2 and sys.argv[2] == "bwd":
+    sys.exit(0)
 for persist, scat in [(8, 0), (8, 2), (6, 2), (5, 2), (4, 2), (4, 3), (4, 0), (3, 3), (6, 1)]:
     core.C.check(lib.iris_set_option(b"persist_ctas_per_sm", persist))
     core.C.check(lib.iris_set_option(b"scatter_ctas_per_sm", scat))
