@@ -86,28 +86,12 @@ __device__ __forceinline__ void field_level_weights(const FieldLevel &L, f3 x, f
     for (int c = 0; c < 8; ++c) w[c] = xmul(xmul((c & 1) ? wx1 : wx0, (c & 2) ? wy1 : wy0), (c & 4) ? wz1 : wz0);
 }
 
-// A/B switch: hashed levels >= FIELD_FINE_NOALLOC load with L1::no_allocate (their sectors are never reused within an SM; keeping them
-// out of L1 was meant to protect the lines of the coarser levels).  Measured: see DESIGN.md section 5; default off.
-#ifndef FIELD_FINE_NOALLOC
-#define FIELD_FINE_NOALLOC 99
-#endif
 template <int DENSE_L>
 __device__ __forceinline__ void field_level_gather(const __half2 *__restrict__ grid, f3 x, int l, __half2 v[8], bool pair = true) {
     const FieldLevel L = c_levels[l];
     uint32_t idx[8];
     float w[8];
     field_level_indices<DENSE_L>(L, x, idx, w);
-#if FIELD_FINE_NOALLOC < 32
-    if (DENSE_L < 0 && l >= FIELD_FINE_NOALLOC) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t r;
-            asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(grid + L.offset + idx[c]));
-            v[c] = *reinterpret_cast<__half2 *>(&r);
-        }
-        return;
-    }
-#endif
     // volatile asm keeps the gathers of a whole group in program order ahead of their consumers (ptxas otherwise sinks every load
     // next to its use to save registers, leaving one or two requests in flight per lane)
 #ifndef FIELD_GATHER_NO_V2

@@ -136,18 +136,8 @@ __device__ __forceinline__ bool tri_test(f3 o, f3 d, float rdd, f3 v0, f3 e1, f3
     return true;
 }
 
-// A/B switch IRIS_TRI_NOALLOC: triangle records loaded with L1::no_allocate (nodes keep the L1).  Measured: DESIGN.md section 5; default off.
-__device__ __forceinline__ float4 ldg4_tri(const float4 *p) {
-#if defined(IRIS_TRI_NOALLOC) && !defined(IRIS_HOST_EMULATION)
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-#else
-    return ldg4(p);
-#endif
-}
 __device__ __forceinline__ void load_tri(const SceneView &S, int32_t slot, f3 &v0, f3 &e1, f3 &e2, int32_t &prim) {
-    const float4 a = ldg4_tri(S.tris + 3 * (int64_t)slot), b = ldg4_tri(S.tris + 3 * (int64_t)slot + 1), c = ldg4_tri(S.tris + 3 * (int64_t)slot + 2);
+    const float4 a = ldg4(S.tris + 3 * (int64_t)slot), b = ldg4(S.tris + 3 * (int64_t)slot + 1), c = ldg4(S.tris + 3 * (int64_t)slot + 2);
     v0 = mk3(a.x, a.y, a.z);
     e1 = mk3(a.w, b.x, b.y);
     e2 = mk3(b.z, b.w, c.x);
