@@ -727,6 +727,28 @@ def test_fused_tcgen05_adjoint_equals_two_kernel_adjoint(small):
             assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()) + 1e-30, (n, sl)
 
 
+def test_capped_scatter_grid_equals_full_grid(small):
+    """`scatter_ctas_per_sm` caps the grid of the grid-gradient scatter (it then strides over the samples; kept for the two-stream
+    overlap experiments of DESIGN.md section 5): same gradient up to the order of the atomics."""
+    from iris_b200 import core
+    lib = core.C.lib()
+    dev = small["dev"]
+    lo, hi = small["sc"].voxel_bounds()
+    g = torch.Generator().manual_seed(5)
+    n = 300_001                                              # > 148 * 256 samples: a capped grid really loops
+    x = (lo + (hi - lo) * torch.rand(n, 3, generator=g)).to(dev)
+    dmat = torch.randn(n, 5, generator=g).to(dev)
+    mat, enc = core.field_forward(small["tables"], x, want_encoded=True)
+    ref = core.field_backward(small["tables"], x, dmat, encoded=enc)
+    try:
+        for cap in (1, 3):
+            core.C.check(lib.iris_set_option(b"scatter_ctas_per_sm", cap))
+            got = core.field_backward(small["tables"], x, dmat, encoded=enc)
+            assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), cap
+    finally:
+        core.C.check(lib.iris_set_option(b"scatter_ctas_per_sm", 0))
+
+
 def test_device_lbvh_builder_gives_identical_hits():
     """builder = 1 (Morton LBVH built entirely on the device) must return bit-identical hits: traversal is exact, the builder
     only changes which boxes are visited."""
