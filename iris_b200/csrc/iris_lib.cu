@@ -88,6 +88,7 @@ static int g_bake_impl = 2;        // 2: persistent warps with the generator / r
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
 static int g_wave_compact = 1;     // 1: live-lane lists (dense queues, dead lanes cost nothing), 0: every kernel over all lanes (A/B)
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
+static int g_tc5_bwd_ctas = 2;     // fused field adjoint: CTAs per SM (98 KB of shared memory each)
 static int g_scatter_ctas = 0;     // > 0: cap the grid of the grid-gradient scatter at this many CTAs per SM (it strides over the samples)
 static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
 static int g_field_impl = 1;   // 1: tcgen05 / TMEM 128-row tiles (default), 0: mma.sync warp tiles (kept for A/B measurements)
@@ -259,6 +260,7 @@ int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
     if (name && std::strcmp(name, "persist_ctas_per_sm") == 0 && value >= 1 && value <= 16) { g_persist_ctas = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "tc5_bwd_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_tc5_bwd_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "scatter_ctas_per_sm") == 0 && value >= 0 && value <= 8) { g_scatter_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "tc5_ctas_per_sm") == 0 && value >= 1 && value <= 8) { g_tc5_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "field_smem_carveout_pct") == 0 && value >= 0 && value <= 100) {
@@ -607,7 +609,7 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
             if (rc2 == IRIS_OK) rc2 = make_row_tile_map(&tm_dx, act.dx, m);
             if (rc2) return rc2;
             ProfScope ps(K_FIELD_BACKWARD_TC5, st);
-            const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * 2);
+            const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * g_tc5_bwd_ctas);
             if (r5) k_field_backward_tc5v2<true><<<gf, BT6_THREADS, BT6_SMEM_BYTES, st>>>(tm_x, tm_dx, *P, m, r5 + c0, d_mat + 5 * c0, act.s, d_params);
             else k_field_backward_tc5v2<false><<<gf, BT6_THREADS, BT6_SMEM_BYTES, st>>>(tm_x, tm_dx, *P, m, nullptr, d_mat + 5 * c0, act.s, d_params);
         } else if (fused) {
@@ -618,7 +620,7 @@ static int run_field_backward(const IrisShadeParams *P, int64_t n, const float *
                 fattr[cur_dev & 63] = true;
             }
             ProfScope ps(K_FIELD_BACKWARD_TC5, st);
-            const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * 2);
+            const unsigned gf = (unsigned)std::min<int64_t>((m + TC5_ROWS - 1) / TC5_ROWS, (int64_t)g_sm_count * g_tc5_bwd_ctas);
             if (r5) k_field_backward_tc5<true><<<gf, TC5_ROWS, BT5_SMEM_BYTES, st>>>(*P, m, r5 + c0, d_mat + 5 * c0, act.X, act.dx, act.s, d_params);
             else k_field_backward_tc5<false><<<gf, TC5_ROWS, BT5_SMEM_BYTES, st>>>(*P, m, nullptr, d_mat + 5 * c0, act.X, act.dx, act.s, d_params);
         } else {
