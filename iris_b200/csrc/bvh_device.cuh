@@ -1,7 +1,7 @@
 // bvh_device.cuh -- on-device builder (builder = 1): Morton-ordered LBVH (Karras 2012) -> greedy collapse to 8-wide ->
 // octant slot assignment -> conservative 8-bit quantisation, producing exactly the node / triangle layout of bvh8.h.
-// Milliseconds instead of the host builder's ~0.7 s per million triangles; tree quality is LBVH (no SAH), so traversal is
-// somewhat slower -- the host binned-SAH builder stays the default for static scenes, this one is for scenes that change.
+// Milliseconds instead of the host builder's ~0.7 s per million triangles.  The lower levels (subtrees of <= IRIS_SAH_TREELET
+// primitives) are rebuilt with a binned SAH in shared memory (k_lbvh_sah_treelets); the levels above them are the Morton splits.
 // Hit results do not depend on the builder: traversal is exact (tests run both).
 #pragma once
 #include <cub/cub.cuh>
@@ -141,6 +141,209 @@ __global__ void k_lbvh_hierarchy(const unsigned long long *__restrict__ keys, in
     N.parent[left] = i;
     N.parent[right] = i;
     if (i == 0) N.parent[0] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// SAH treelets.  The Morton hierarchy is good at the top (spatial median splits of the whole scene) and poor at the bottom, where
+// neighbouring triangles of different size and shape are grouped by centroid code alone (on a scan-like mesh the host binned-SAH tree
+// traces ~10 % faster, profiles/r2l_*).  Every subtree of at most IRIS_SAH_TREELET primitives whose parent is larger is therefore
+// REBUILT by one CTA with a binned SAH (8 bins x 3 axes over the centroids, cost = area x count) entirely in shared memory: the
+// subtree's primitives are re-ordered inside their range of the sorted array and its internal nodes re-linked, using the same
+// numbering rule as the radix tree (split after sorted position g: an internal left child is node g, an internal right child node
+// g + 1), so the ids stay unique, the subtree's root keeps its id, and the fit / collapse passes below see an ordinary tree.
+// ------------------------------------------------------------------------------------------------------------------------
+#ifndef IRIS_SAH_TREELET
+#define IRIS_SAH_TREELET 4096     // primitives per rebuilt subtree (44 B of shared memory each); 0: plain LBVH
+#endif
+#define SAH_BINS 8
+#define SAH_THREADS 128
+#define SAH_SMEM_BYTES(T) ((size_t)(T) * 44)
+
+__device__ __forceinline__ int sah_f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float sah_ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void k_lbvh_treelet_roots(int n, LbvhNodes N, int T, int *list, int *count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 r = N.range[i];
+    const int c = r.y - r.x + 1;
+    if (c > T || c < 4) return;
+    const int p = N.parent[i];
+    if (p >= 0) {
+        const int2 pr = N.range[p];
+        if (pr.y - pr.x + 1 <= T) return;
+    }
+    list[atomicAdd(count, 1)] = i;
+}
+
+template <int T>
+__global__ void __launch_bounds__(SAH_THREADS) k_lbvh_sah_treelets(const int *__restrict__ list, int n_list, int n, LbvhNodes N,
+                                                                   const DBox *__restrict__ tbox, uint32_t *sorted) {
+    extern __shared__ __align__(16) unsigned char sah_smem[];    // 44 bytes per primitive: T = 1024 -> 44 KB, 4096 -> 176 KB
+    float (*s_c)[T] = reinterpret_cast<float (*)[T]>(sah_smem);
+    float (*s_lo)[T] = s_c + 3, (*s_hi)[T] = s_c + 6;
+    uint32_t *s_id = reinterpret_cast<uint32_t *>(s_c + 9);
+    uint16_t *s_ord = reinterpret_cast<uint16_t *>(s_id + T), *s_ord2 = s_ord + T;
+    __shared__ int s_bins[3][SAH_BINS][7];      // count | lo xyz | hi xyz (order-preserving int images of the floats)
+    __shared__ int s_cb[6];
+    __shared__ int s_split[3];                  // axis (-1: none), bin, primitives on the left
+    __shared__ int s_warp[2 * (SAH_THREADS / 32)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = blockIdx.x; t < n_list; t += gridDim.x) {
+        const int root = list[t];
+        const int2 rr = N.range[root];
+        const int a = rr.x, m = rr.y - rr.x + 1;
+        __syncthreads();
+        for (int k = tid; k < m; k += SAH_THREADS) {
+            const uint32_t id = sorted[a + k];
+            const DBox b = tbox[id];
+            s_id[k] = id;
+            for (int ax = 0; ax < 3; ++ax) { s_lo[ax][k] = b.lo[ax]; s_hi[ax][k] = b.hi[ax]; s_c[ax][k] = 0.5f * (b.lo[ax] + b.hi[ax]); }
+            s_ord[k] = (uint16_t)k;
+        }
+        __syncthreads();
+        // iterative top-down build; (f, l, id) and the stack are block-uniform
+        int3 stack[24];
+        int sp = 0;
+        int f = 0, l = m - 1, id = root;
+        for (;;) {
+            const int c = l - f + 1;
+            int n_l = c >> 1;                                       // default: split the current order in the middle
+            if (c > 3) {
+                if (tid < 6) s_cb[tid] = tid < 3 ? 0x7FFFFFFF : (int)0x80000000;
+                for (int k = tid; k < 3 * SAH_BINS * 7; k += SAH_THREADS) {
+                    const int w = k % 7;
+                    (&s_bins[0][0][0])[k] = w == 0 ? 0 : (w < 4 ? 0x7FFFFFFF : (int)0x80000000);
+                }
+                __syncthreads();
+                for (int k = f + tid; k <= l; k += SAH_THREADS) {
+                    const int j = s_ord[k];
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const int o = sah_f2ord(s_c[ax][j]);
+                        atomicMin(&s_cb[ax], o);
+                        atomicMax(&s_cb[3 + ax], o);
+                    }
+                }
+                __syncthreads();
+                float c0[3], sc[3];
+                for (int ax = 0; ax < 3; ++ax) {
+                    c0[ax] = sah_ord2f(s_cb[ax]);
+                    const float ext = sah_ord2f(s_cb[3 + ax]) - c0[ax];
+                    sc[ax] = ext > 0.f ? (float)SAH_BINS / ext : 0.f;
+                }
+                for (int k = f + tid; k <= l; k += SAH_THREADS) {
+                    const int j = s_ord[k];
+                    for (int ax = 0; ax < 3; ++ax) {
+                        if (!(sc[ax] > 0.f)) continue;
+                        const int b = min(SAH_BINS - 1, max(0, (int)((s_c[ax][j] - c0[ax]) * sc[ax])));
+                        int *B = s_bins[ax][b];
+                        atomicAdd(B, 1);
+                        for (int d = 0; d < 3; ++d) {
+                            atomicMin(B + 1 + d, sah_f2ord(s_lo[d][j]));
+                            atomicMax(B + 4 + d, sah_f2ord(s_hi[d][j]));
+                        }
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    float cost = INFINITY;
+                    int nl = 0;
+                    if (lane < 3 * (SAH_BINS - 1)) {
+                        const int ax = lane / (SAH_BINS - 1), kb = lane % (SAH_BINS - 1);
+                        if (sc[ax] > 0.f) {
+                            float lo0[3] = {INFINITY, INFINITY, INFINITY}, hi0[3] = {-INFINITY, -INFINITY, -INFINITY};
+                            float lo1[3] = {INFINITY, INFINITY, INFINITY}, hi1[3] = {-INFINITY, -INFINITY, -INFINITY};
+                            int n0 = 0, n1 = 0;
+                            for (int b = 0; b < SAH_BINS; ++b) {
+                                const int *B = s_bins[ax][b];
+                                if (B[0] == 0) continue;
+                                if (b <= kb) {
+                                    n0 += B[0];
+                                    for (int d = 0; d < 3; ++d) { lo0[d] = fminf(lo0[d], sah_ord2f(B[1 + d])); hi0[d] = fmaxf(hi0[d], sah_ord2f(B[4 + d])); }
+                                } else {
+                                    n1 += B[0];
+                                    for (int d = 0; d < 3; ++d) { lo1[d] = fminf(lo1[d], sah_ord2f(B[1 + d])); hi1[d] = fmaxf(hi1[d], sah_ord2f(B[4 + d])); }
+                                }
+                            }
+                            if (n0 > 0 && n1 > 0) {
+                                const float e0x = hi0[0] - lo0[0], e0y = hi0[1] - lo0[1], e0z = hi0[2] - lo0[2];
+                                const float e1x = hi1[0] - lo1[0], e1y = hi1[1] - lo1[1], e1z = hi1[2] - lo1[2];
+                                cost = (e0x * e0y + e0y * e0z + e0z * e0x) * (float)n0 + (e1x * e1y + e1y * e1z + e1z * e1x) * (float)n1;
+                                nl = n0;
+                            }
+                        }
+                    }
+                    int best = lane;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float oc = __shfl_xor_sync(0xffffffffu, cost, o);
+                        const int ob = __shfl_xor_sync(0xffffffffu, best, o), on = __shfl_xor_sync(0xffffffffu, nl, o);
+                        if (oc < cost || (oc == cost && ob < best)) { cost = oc; best = ob; nl = on; }
+                    }
+                    if (lane == 0) {
+                        const bool ok = cost < INFINITY;
+                        s_split[0] = ok ? best / (SAH_BINS - 1) : -1;
+                        s_split[1] = best % (SAH_BINS - 1);
+                        s_split[2] = nl;
+                    }
+                }
+                __syncthreads();
+                const int ax = s_split[0], kb = s_split[1];
+                if (ax >= 0) {
+                    n_l = s_split[2];
+                    int run_l = 0, run_r = 0;
+                    for (int base = f; base <= l; base += SAH_THREADS) {
+                        const int k = base + tid;
+                        const bool in = k <= l;
+                        int j = 0;
+                        bool left = false;
+                        if (in) {
+                            j = s_ord[k];
+                            left = min(SAH_BINS - 1, max(0, (int)((s_c[ax][j] - c0[ax]) * sc[ax]))) <= kb;
+                        }
+                        const unsigned bl = __ballot_sync(0xffffffffu, in && left), br = __ballot_sync(0xffffffffu, in && !left);
+                        if (lane == 0) { s_warp[warp] = __popc(bl); s_warp[SAH_THREADS / 32 + warp] = __popc(br); }
+                        __syncthreads();
+                        int pl = 0, pr = 0, tl = 0, tr = 0;
+                        for (int w = 0; w < SAH_THREADS / 32; ++w) {
+                            const int x = s_warp[w], y = s_warp[SAH_THREADS / 32 + w];
+                            if (w < warp) { pl += x; pr += y; }
+                            tl += x; tr += y;
+                        }
+                        const unsigned lt = (1u << lane) - 1u;
+                        if (in) {
+                            const int pos = left ? f + run_l + pl + __popc(bl & lt) : f + n_l + run_r + pr + __popc(br & lt);
+                            s_ord2[pos] = (uint16_t)j;
+                        }
+                        run_l += tl;
+                        run_r += tr;
+                        __syncthreads();
+                    }
+                    for (int k = f + tid; k <= l; k += SAH_THREADS) s_ord[k] = s_ord2[k];
+                    __syncthreads();
+                }
+            }
+            const int mid = f + n_l, n_r = c - n_l;
+            const int left_id = n_l == 1 ? n - 1 + a + f : a + mid - 1;
+            const int right_id = n_r == 1 ? n - 1 + a + mid : a + mid;
+            if (tid == 0) {
+                N.child[id] = make_int2(left_id, right_id);
+                N.range[id] = make_int2(a + f, a + l);
+                N.parent[left_id] = id;
+                N.parent[right_id] = id;
+            }
+            // continue with the smaller side, park the larger one (stack depth <= log2 T)
+            const bool go_left_first = n_l <= n_r;
+            const int3 L = make_int3(f, mid - 1, left_id), R = make_int3(mid, l, right_id);
+            const int3 first = go_left_first ? L : R, second = go_left_first ? R : L;
+            if (second.y > second.x) stack[sp++] = second;
+            if (first.y > first.x) { f = first.x; l = first.y; id = first.z; continue; }
+            if (sp == 0) break;
+            const int3 nx = stack[--sp];
+            f = nx.x; l = nx.y; id = nx.z;
+        }
+        __syncthreads();
+        for (int k = tid; k < m; k += SAH_THREADS) sorted[a + k] = s_id[s_ord[k]];
+    }
 }
 
 __global__ void k_lbvh_fit(const DBox *__restrict__ tbox, const uint32_t *__restrict__ sorted, int n, const float *__restrict__ bounds, LbvhNodes N) {

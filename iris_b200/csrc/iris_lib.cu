@@ -88,6 +88,7 @@ static int g_bake_impl = 2;        // 2: persistent warps with the generator / r
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
 static int g_wave_compact = 1;     // 1: live-lane lists (dense queues, dead lanes cost nothing), 0: every kernel over all lanes (A/B)
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
+static int g_sah_treelets = 1;     // device builder: rebuild the lower levels with a binned SAH (bvh_device.cuh); 0 = plain LBVH
 static int g_tc5_bwd_ctas = 2;     // fused field adjoint: CTAs per SM (98 KB of shared memory each)
 static int g_scatter_ctas = 0;     // > 0: cap the grid of the grid-gradient scatter at this many CTAs per SM (it strides over the samples)
 static int g_persist_ctas = 8;     // resident CTAs per SM for the persistent grid
@@ -154,7 +155,7 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     LbvhNodes N{};
-    int *d_wide_bin = nullptr, *d_wide_depth = nullptr, *d_counters = nullptr;
+    int *d_wide_bin = nullptr, *d_wide_depth = nullptr, *d_counters = nullptr, *d_list = nullptr, *d_nlist = nullptr;
     Bvh8Node *d_wide = nullptr;
     int counters[3] = {1, 0, 1};
     const float binit[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -186,6 +187,20 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
     CUDA_OK(cudaMemset(N.flag, 0, sizeof(int) * (size_t)n));
     CUDA_OK(cudaMemset(N.parent, 0xFF, sizeof(int) * 2 * (size_t)n));
     if (n > 1) k_lbvh_hierarchy<<<gb, 256>>>(d_keys2, n, N);
+#if IRIS_SAH_TREELET > 0
+    if (n > 3 && g_sah_treelets) {                               // binned-SAH rebuild of the subtrees of <= IRIS_SAH_TREELET primitives
+        int n_list = 0;
+        CUDA_OK(cudaMalloc(&d_list, sizeof(int) * (size_t)n));
+        CUDA_OK(cudaMalloc(&d_nlist, sizeof(int)));
+        CUDA_OK(cudaMemset(d_nlist, 0, sizeof(int)));
+        k_lbvh_treelet_roots<<<gb, 256>>>(n, N, IRIS_SAH_TREELET, d_list, d_nlist);
+        CUDA_OK(cudaMemcpy(&n_list, d_nlist, sizeof(int), cudaMemcpyDeviceToHost));
+        if (n_list > 0) {
+            CUDA_OK(cudaFuncSetAttribute(k_lbvh_sah_treelets<IRIS_SAH_TREELET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SAH_SMEM_BYTES(IRIS_SAH_TREELET)));
+            k_lbvh_sah_treelets<IRIS_SAH_TREELET><<<(unsigned)std::min(n_list, 148 * 16), SAH_THREADS, SAH_SMEM_BYTES(IRIS_SAH_TREELET)>>>(d_list, n_list, n, N, d_tbox, d_idx2);
+        }
+    }
+#endif
     k_lbvh_fit<<<gb, 256>>>(d_tbox, d_idx2, n, d_bounds, N);
     CUDA_OK(cudaMalloc(&d_wide, sizeof(Bvh8Node) * (size_t)n));
     CUDA_OK(cudaMalloc(&d_wide_bin, sizeof(int) * (size_t)n));
@@ -221,7 +236,7 @@ done:
     cudaFree(d_verts); cudaFree(d_faces); cudaFree(d_recs); cudaFree(d_tris); cudaFree(d_tbox); cudaFree(d_bounds);
     cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_tmp);
     cudaFree(N.child); cudaFree(N.range); cudaFree(N.parent); cudaFree(N.box); cudaFree(N.flag);
-    cudaFree(d_wide); cudaFree(d_wide_bin); cudaFree(d_wide_depth); cudaFree(d_counters);
+    cudaFree(d_wide); cudaFree(d_wide_bin); cudaFree(d_wide_depth); cudaFree(d_counters); cudaFree(d_list); cudaFree(d_nlist);
     return e;
 }
 
@@ -260,6 +275,7 @@ int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
     if (name && std::strcmp(name, "persist_ctas_per_sm") == 0 && value >= 1 && value <= 16) { g_persist_ctas = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "lbvh_sah_treelets") == 0 && (value == 0 || value == 1)) { g_sah_treelets = value; return IRIS_OK; }
     if (name && std::strcmp(name, "tc5_bwd_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_tc5_bwd_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "scatter_ctas_per_sm") == 0 && value >= 0 && value <= 8) { g_scatter_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "tc5_ctas_per_sm") == 0 && value >= 1 && value <= 8) { g_tc5_ctas = value; return IRIS_OK; }
