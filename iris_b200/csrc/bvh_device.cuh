@@ -147,7 +147,7 @@ __global__ void k_lbvh_hierarchy(const unsigned long long *__restrict__ keys, in
 // SAH treelets.  The Morton hierarchy is good at the top (spatial median splits of the whole scene) and poor at the bottom, where
 // neighbouring triangles of different size and shape are grouped by centroid code alone (on a scan-like mesh the host binned-SAH tree
 // traces ~10 % faster, profiles/r2l_*).  Every subtree of at most IRIS_SAH_TREELET primitives whose parent is larger is therefore
-// REBUILT by one CTA with a binned SAH (8 bins x 3 axes over the centroids, cost = area x count) entirely in shared memory: the
+// REBUILT by one CTA with a binned SAH (SAH_BINS bins x 3 axes over the centroids, cost = area x count) entirely in shared memory: the
 // subtree's primitives are re-ordered inside their range of the sorted array and its internal nodes re-linked, using the same
 // numbering rule as the radix tree (split after sorted position g: an internal left child is node g, an internal right child node
 // g + 1), so the ids stay unique, the subtree's root keeps its id, and the fit / collapse passes below see an ordinary tree.
@@ -155,7 +155,9 @@ __global__ void k_lbvh_hierarchy(const unsigned long long *__restrict__ keys, in
 #ifndef IRIS_SAH_TREELET
 #define IRIS_SAH_TREELET 4096     // primitives per rebuilt subtree (44 B of shared memory each); 0: plain LBVH
 #endif
-#define SAH_BINS 8
+#ifndef SAH_BINS
+#define SAH_BINS 16
+#endif
 #define SAH_THREADS 128
 #define SAH_SMEM_BYTES(T) ((size_t)(T) * 44)
 
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(SAH_THREADS) k_lbvh_sah_treelets(const int *__
     __shared__ int s_bins[3][SAH_BINS][7];      // count | lo xyz | hi xyz (order-preserving int images of the floats)
     __shared__ int s_cb[6];
     __shared__ int s_split[3];                  // axis (-1: none), bin, primitives on the left
+    __shared__ float s_cost[3 * (SAH_BINS - 1)];
+    __shared__ int s_nl[3 * (SAH_BINS - 1)];
     __shared__ int s_warp[2 * (SAH_THREADS / 32)];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = blockIdx.x; t < n_list; t += gridDim.x) {
@@ -245,45 +249,52 @@ __global__ void __launch_bounds__(SAH_THREADS) k_lbvh_sah_treelets(const int *__
                     }
                 }
                 __syncthreads();
-                if (warp == 0) {
+                // one thread per candidate (axis, last bin on the left), then the minimum over the candidates by warp 0
+                if (tid < 3 * (SAH_BINS - 1)) {
                     float cost = INFINITY;
                     int nl = 0;
-                    if (lane < 3 * (SAH_BINS - 1)) {
-                        const int ax = lane / (SAH_BINS - 1), kb = lane % (SAH_BINS - 1);
-                        if (sc[ax] > 0.f) {
-                            float lo0[3] = {INFINITY, INFINITY, INFINITY}, hi0[3] = {-INFINITY, -INFINITY, -INFINITY};
-                            float lo1[3] = {INFINITY, INFINITY, INFINITY}, hi1[3] = {-INFINITY, -INFINITY, -INFINITY};
-                            int n0 = 0, n1 = 0;
-                            for (int b = 0; b < SAH_BINS; ++b) {
-                                const int *B = s_bins[ax][b];
-                                if (B[0] == 0) continue;
-                                if (b <= kb) {
-                                    n0 += B[0];
-                                    for (int d = 0; d < 3; ++d) { lo0[d] = fminf(lo0[d], sah_ord2f(B[1 + d])); hi0[d] = fmaxf(hi0[d], sah_ord2f(B[4 + d])); }
-                                } else {
-                                    n1 += B[0];
-                                    for (int d = 0; d < 3; ++d) { lo1[d] = fminf(lo1[d], sah_ord2f(B[1 + d])); hi1[d] = fmaxf(hi1[d], sah_ord2f(B[4 + d])); }
-                                }
-                            }
-                            if (n0 > 0 && n1 > 0) {
-                                const float e0x = hi0[0] - lo0[0], e0y = hi0[1] - lo0[1], e0z = hi0[2] - lo0[2];
-                                const float e1x = hi1[0] - lo1[0], e1y = hi1[1] - lo1[1], e1z = hi1[2] - lo1[2];
-                                cost = (e0x * e0y + e0y * e0z + e0z * e0x) * (float)n0 + (e1x * e1y + e1y * e1z + e1z * e1x) * (float)n1;
-                                nl = n0;
+                    const int ax = tid / (SAH_BINS - 1), kb = tid % (SAH_BINS - 1);
+                    if (sc[ax] > 0.f) {
+                        float lo0[3] = {INFINITY, INFINITY, INFINITY}, hi0[3] = {-INFINITY, -INFINITY, -INFINITY};
+                        float lo1[3] = {INFINITY, INFINITY, INFINITY}, hi1[3] = {-INFINITY, -INFINITY, -INFINITY};
+                        int n0 = 0, n1 = 0;
+                        for (int b = 0; b < SAH_BINS; ++b) {
+                            const int *B = s_bins[ax][b];
+                            if (B[0] == 0) continue;
+                            if (b <= kb) {
+                                n0 += B[0];
+                                for (int d = 0; d < 3; ++d) { lo0[d] = fminf(lo0[d], sah_ord2f(B[1 + d])); hi0[d] = fmaxf(hi0[d], sah_ord2f(B[4 + d])); }
+                            } else {
+                                n1 += B[0];
+                                for (int d = 0; d < 3; ++d) { lo1[d] = fminf(lo1[d], sah_ord2f(B[1 + d])); hi1[d] = fmaxf(hi1[d], sah_ord2f(B[4 + d])); }
                             }
                         }
+                        if (n0 > 0 && n1 > 0) {
+                            const float e0x = hi0[0] - lo0[0], e0y = hi0[1] - lo0[1], e0z = hi0[2] - lo0[2];
+                            const float e1x = hi1[0] - lo1[0], e1y = hi1[1] - lo1[1], e1z = hi1[2] - lo1[2];
+                            cost = (e0x * e0y + e0y * e0z + e0z * e0x) * (float)n0 + (e1x * e1y + e1y * e1z + e1z * e1x) * (float)n1;
+                            nl = n0;
+                        }
                     }
-                    int best = lane;
+                    s_cost[tid] = cost;
+                    s_nl[tid] = nl;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    float cost = INFINITY;
+                    int best = 0;
+                    for (int k = lane; k < 3 * (SAH_BINS - 1); k += 32)
+                        if (s_cost[k] < cost) { cost = s_cost[k]; best = k; }
                     for (int o = 16; o > 0; o >>= 1) {
                         const float oc = __shfl_xor_sync(0xffffffffu, cost, o);
-                        const int ob = __shfl_xor_sync(0xffffffffu, best, o), on = __shfl_xor_sync(0xffffffffu, nl, o);
-                        if (oc < cost || (oc == cost && ob < best)) { cost = oc; best = ob; nl = on; }
+                        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        if (oc < cost || (oc == cost && ob < best)) { cost = oc; best = ob; }
                     }
                     if (lane == 0) {
                         const bool ok = cost < INFINITY;
                         s_split[0] = ok ? best / (SAH_BINS - 1) : -1;
                         s_split[1] = best % (SAH_BINS - 1);
-                        s_split[2] = nl;
+                        s_split[2] = s_nl[best];
                     }
                 }
                 __syncthreads();
