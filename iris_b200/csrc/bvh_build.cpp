@@ -36,6 +36,7 @@ constexpr int kBins = 16;
 constexpr int kMaxLeaf = IRIS_MAX_LEAF;
 
 struct Builder {
+    int32_t max_leaf = kMaxLeaf;   // 1: split down to single primitives (top tree over clusters, host_sah_top)
     std::vector<Box> tbox;
     std::vector<float> cent;   // 3 per tri
     std::vector<int32_t> order;
@@ -93,7 +94,7 @@ struct Builder {
                 }
             }
             float leaf_cost = b.area() * j.count;
-            bool make_leaf = j.count <= kMaxLeaf && (best_axis < 0 || best_cost + b.area() >= leaf_cost);
+            bool make_leaf = j.count <= max_leaf && (best_axis < 0 || best_cost + b.area() >= leaf_cost);
             if (make_leaf) { nodes[j.node].left = j.first; nodes[j.node].count = j.count; continue; }
             int32_t mid;
             if (best_axis >= 0) {
@@ -315,4 +316,53 @@ void host_bvh_free(HostBvh *b) {
     std::free(b->tris);
     b->nodes = nullptr;
     b->tris = nullptr;
+}
+
+
+// Top of the device builder's tree (bvh_device.cuh): binned SAH over the boxes of C clusters (subtrees of the Morton hierarchy with at
+// most IRIS_SAH_TREELET primitives -- a few hundred to a few thousand boxes), split down to single clusters.  Returns the clusters in
+// tree order (`order`, C entries) and the internal nodes in pre-order: node k covers order[first[k] .. first[k] + count[k]) and splits
+// after its first nleft[k] clusters; left[k] / right[k] = index of the child node, or -1 - (position in order) when the child is one cluster.
+int host_sah_top(const float *boxes, int32_t C, int32_t *order, int32_t *first, int32_t *count, int32_t *nleft, int32_t *left, int32_t *right) {
+    if (C < 2) return 0;
+    Builder B;
+    B.max_leaf = 1;
+    B.tbox.resize((size_t)C);
+    B.cent.resize((size_t)C * 3);
+    B.order.resize((size_t)C);
+    for (int32_t c = 0; c < C; ++c) {
+        for (int k = 0; k < 3; ++k) {
+            B.tbox[(size_t)c].lo[k] = boxes[6 * (size_t)c + k];
+            B.tbox[(size_t)c].hi[k] = boxes[6 * (size_t)c + 3 + k];
+            B.cent[3 * (size_t)c + k] = 0.5f * (boxes[6 * (size_t)c + k] + boxes[6 * (size_t)c + 3 + k]);
+        }
+        B.order[(size_t)c] = c;
+    }
+    B.nodes.reserve((size_t)(2 * C + 2));
+    B.nodes.push_back(Node2());
+    B.build_range(0, 0, C);
+    for (int32_t c = 0; c < C; ++c) order[c] = B.order[(size_t)c];
+    // pre-order numbering of the internal nodes
+    std::vector<int32_t> id_of(B.nodes.size(), -1), st;
+    int32_t n_inner = 0;
+    st.push_back(0);
+    while (!st.empty()) {
+        const int32_t n2 = st.back();
+        st.pop_back();
+        if (B.nodes[(size_t)n2].count != 0) continue;          // a single cluster
+        id_of[(size_t)n2] = n_inner++;
+        st.push_back(B.nodes[(size_t)n2].left + 1);
+        st.push_back(B.nodes[(size_t)n2].left);
+    }
+    for (size_t n2 = 0; n2 < B.nodes.size(); ++n2) {
+        const int32_t k = id_of[n2];
+        if (k < 0) continue;
+        const Node2 &nd = B.nodes[n2], &L = B.nodes[(size_t)nd.left], &R = B.nodes[(size_t)nd.left + 1];
+        first[k] = nd.first;
+        count[k] = nd.total;
+        nleft[k] = L.total;
+        left[k] = L.count != 0 ? -1 - L.first : id_of[(size_t)nd.left];
+        right[k] = R.count != 0 ? -1 - R.first : id_of[(size_t)nd.left + 1];
+    }
+    return n_inner;                                            // == C - 1
 }

@@ -178,6 +178,52 @@ __global__ void k_lbvh_treelet_roots(int n, LbvhNodes N, int T, int *list, int *
     list[atomicAdd(count, 1)] = i;
 }
 
+// ---- top of the tree: the maximal subtrees of <= T primitives ("clusters", single leaves included) tile the sorted array; their boxes
+//      go to the host, which builds a SAH tree over the few hundred / thousand of them (host_sah_top) and sends back the new cluster
+//      order and the top nodes; the clusters are moved to their new places and the top nodes re-linked with the radix-tree numbering.
+__global__ void k_lbvh_clusters(int n, LbvhNodes N, int T, int2 *out, int *count) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= 2 * n - 1) return;
+    int start, cnt;
+    if (node >= n - 1) { start = node - (n - 1); cnt = 1; } else { const int2 r = N.range[node]; start = r.x; cnt = r.y - r.x + 1; }
+    if (cnt > T) return;
+    const int p = N.parent[node];
+    if (p >= 0) {
+        const int2 pr = N.range[p];
+        if (pr.y - pr.x + 1 <= T) return;
+    }
+    out[atomicAdd(count, 1)] = make_int2(start, cnt);
+}
+__global__ void k_lbvh_cluster_boxes(const int2 *__restrict__ cl, int C, const DBox *__restrict__ tbox, const uint32_t *__restrict__ sorted, float *cbox) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = lane; k < cl[c].y; k += 32) {
+        const DBox b = tbox[sorted[cl[c].x + k]];
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], b.lo[a]); hi[a] = fmaxf(hi[a], b.hi[a]); }
+    }
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+    if (lane == 0)
+        for (int a = 0; a < 3; ++a) { cbox[6 * c + a] = lo[a]; cbox[6 * c + 3 + a] = hi[a]; }
+}
+__global__ void k_lbvh_permute(const int3 *__restrict__ perm /* old start, size, new start */, const uint32_t *__restrict__ src, uint32_t *dst) {
+    const int3 p = perm[blockIdx.x];
+    for (int k = threadIdx.x; k < p.y; k += blockDim.x) dst[p.z + k] = src[p.x + k];
+}
+__global__ void k_lbvh_write_top(const int *__restrict__ rec /* id, left, right, first, last */, int n_rec, const int3 *__restrict__ roots, int n_roots, LbvhNodes N) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_rec) {
+        const int id = rec[5 * k], l = rec[5 * k + 1], r = rec[5 * k + 2];
+        N.child[id] = make_int2(l, r);
+        N.range[id] = make_int2(rec[5 * k + 3], rec[5 * k + 4]);
+        N.parent[l] = id;
+        N.parent[r] = id;
+        if (id == 0) N.parent[0] = -1;
+    }
+    if (k < n_roots) N.range[roots[k].x] = make_int2(roots[k].y, roots[k].z);
+}
+
 template <int T>
 __global__ void __launch_bounds__(SAH_THREADS) k_lbvh_sah_treelets(const int *__restrict__ list, int n_list, int n, LbvhNodes N,
                                                                    const DBox *__restrict__ tbox, uint32_t *sorted) {

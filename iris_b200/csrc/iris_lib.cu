@@ -1,4 +1,5 @@
 // iris_lib.cu -- the C ABI of libiris_b200.so (include/iris_b200.h): argument checking, launches, error strings.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -88,6 +89,7 @@ static int g_bake_impl = 2;        // 2: persistent warps with the generator / r
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
 static int g_wave_compact = 1;     // 1: live-lane lists (dense queues, dead lanes cost nothing), 0: every kernel over all lanes (A/B)
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
+static int g_sah_top = 1;          // device builder: SAH tree over the clusters for the levels above the treelets (host, tiny); 0 = Morton splits
 static int g_sah_treelets = 1;     // device builder: rebuild the lower levels with a binned SAH (bvh_device.cuh); 0 = plain LBVH
 static int g_tc5_bwd_ctas = 2;     // fused field adjoint: CTAs per SM (98 KB of shared memory each)
 static int g_scatter_ctas = 0;     // > 0: cap the grid of the grid-gradient scatter at this many CTAs per SM (it strides over the samples)
@@ -155,7 +157,10 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     LbvhNodes N{};
-    int *d_wide_bin = nullptr, *d_wide_depth = nullptr, *d_counters = nullptr, *d_list = nullptr, *d_nlist = nullptr;
+    int *d_wide_bin = nullptr, *d_wide_depth = nullptr, *d_counters = nullptr, *d_list = nullptr, *d_nlist = nullptr, *d_rec = nullptr;
+    int2 *d_cl = nullptr;
+    int3 *d_perm = nullptr, *d_roots = nullptr;
+    float *d_cbox = nullptr;
     Bvh8Node *d_wide = nullptr;
     int counters[3] = {1, 0, 1};
     const float binit[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -188,13 +193,86 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
     CUDA_OK(cudaMemset(N.parent, 0xFF, sizeof(int) * 2 * (size_t)n));
     if (n > 1) k_lbvh_hierarchy<<<gb, 256>>>(d_keys2, n, N);
 #if IRIS_SAH_TREELET > 0
-    if (n > 3 && g_sah_treelets) {                               // binned-SAH rebuild of the subtrees of <= IRIS_SAH_TREELET primitives
-        int n_list = 0;
+    if (n > 3 && g_sah_treelets) {
+        // binned-SAH rebuild (bvh_device.cuh): top tree over the clusters (host, a few thousand boxes), then every cluster by one CTA
+        int n_list = 0, C = 0;
+        bool top_done = false;
         CUDA_OK(cudaMalloc(&d_list, sizeof(int) * (size_t)n));
         CUDA_OK(cudaMalloc(&d_nlist, sizeof(int)));
         CUDA_OK(cudaMemset(d_nlist, 0, sizeof(int)));
-        k_lbvh_treelet_roots<<<gb, 256>>>(n, N, IRIS_SAH_TREELET, d_list, d_nlist);
-        CUDA_OK(cudaMemcpy(&n_list, d_nlist, sizeof(int), cudaMemcpyDeviceToHost));
+        if (g_sah_top && n > IRIS_SAH_TREELET) {
+            CUDA_OK(cudaMalloc(&d_cl, sizeof(int2) * (size_t)n));
+            k_lbvh_clusters<<<(unsigned)((2 * (size_t)n + 255) / 256), 256>>>(n, N, IRIS_SAH_TREELET, d_cl, d_nlist);
+            CUDA_OK(cudaMemcpy(&C, d_nlist, sizeof(int), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemset(d_nlist, 0, sizeof(int)));
+        }
+        if (C >= 2) {
+            std::vector<int2> cl((size_t)C);
+            std::vector<float> cbox((size_t)C * 6), sbox((size_t)C * 6);
+            CUDA_OK(cudaMalloc(&d_cbox, sizeof(float) * 6 * (size_t)C));
+            k_lbvh_cluster_boxes<<<(unsigned)(((size_t)C * 32 + 255) / 256), 256>>>(d_cl, C, d_tbox, d_idx2, d_cbox);
+            CUDA_OK(cudaMemcpy(cl.data(), d_cl, sizeof(int2) * (size_t)C, cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(cbox.data(), d_cbox, sizeof(float) * 6 * (size_t)C, cudaMemcpyDeviceToHost));
+            std::vector<int32_t> by_start((size_t)C);
+            for (int c = 0; c < C; ++c) by_start[(size_t)c] = c;
+            std::sort(by_start.begin(), by_start.end(), [&](int32_t x, int32_t y) { return cl[(size_t)x].x < cl[(size_t)y].x; });
+            bool tiles = true;                                   // the clusters must tile [0, n) exactly
+            int64_t pos = 0;
+            for (int c = 0; c < C && tiles; ++c) {
+                const int2 q = cl[(size_t)by_start[(size_t)c]];
+                tiles = q.x == pos && q.y >= 1;
+                pos += q.y;
+                for (int k = 0; k < 6; ++k) sbox[6 * (size_t)c + k] = cbox[6 * (size_t)by_start[(size_t)c] + k];
+            }
+            tiles = tiles && pos == n;
+            if (tiles) {
+                std::vector<int32_t> order((size_t)C), tf((size_t)C), tc((size_t)C), tl((size_t)C), tL((size_t)C), tR((size_t)C);
+                const int n_top = host_sah_top(sbox.data(), C, order.data(), tf.data(), tc.data(), tl.data(), tL.data(), tR.data());
+                std::vector<int64_t> P((size_t)C + 1, 0);        // first sorted position of the cluster at tree-order position k
+                std::vector<int3> perm((size_t)C), roots;
+                for (int k = 0; k < C; ++k) {
+                    const int2 q = cl[(size_t)by_start[(size_t)order[(size_t)k]]];
+                    perm[(size_t)k] = make_int3(q.x, q.y, (int)P[(size_t)k]);
+                    P[(size_t)k + 1] = P[(size_t)k] + q.y;
+                }
+                std::vector<int> rec;
+                rec.reserve((size_t)5 * (size_t)n_top);
+                std::vector<std::pair<int32_t, int32_t>> st;      // (top node, its id in the binary tree)
+                st.push_back({0, 0});
+                while (!st.empty()) {
+                    const int32_t k = st.back().first, id = st.back().second;
+                    st.pop_back();
+                    const int32_t f0 = tf[(size_t)k], mid = f0 + tl[(size_t)k], end = f0 + tc[(size_t)k];
+                    const int64_t a0 = P[(size_t)f0], am = P[(size_t)mid], ae = P[(size_t)end];
+                    const int left_id = (am - a0 == 1) ? (int)(n - 1 + a0) : (int)(am - 1);
+                    const int right_id = (ae - am == 1) ? (int)(n - 1 + am) : (int)am;
+                    rec.insert(rec.end(), {(int)id, left_id, right_id, (int)a0, (int)(ae - 1)});
+                    if (tL[(size_t)k] >= 0) st.push_back({tL[(size_t)k], left_id});
+                    else if (am - a0 >= 2) roots.push_back(make_int3(left_id, (int)a0, (int)(am - 1)));
+                    if (tR[(size_t)k] >= 0) st.push_back({tR[(size_t)k], right_id});
+                    else if (ae - am >= 2) roots.push_back(make_int3(right_id, (int)am, (int)(ae - 1)));
+                }
+                std::vector<int> root_ids(roots.size());
+                for (size_t k = 0; k < roots.size(); ++k) root_ids[k] = roots[k].x;
+                CUDA_OK(cudaMalloc(&d_perm, sizeof(int3) * (size_t)C));
+                CUDA_OK(cudaMalloc(&d_rec, sizeof(int) * std::max<size_t>(rec.size(), 1)));
+                CUDA_OK(cudaMalloc(&d_roots, sizeof(int3) * std::max<size_t>(roots.size(), 1)));
+                CUDA_OK(cudaMemcpy(d_perm, perm.data(), sizeof(int3) * (size_t)C, cudaMemcpyHostToDevice));
+                CUDA_OK(cudaMemcpy(d_rec, rec.data(), sizeof(int) * rec.size(), cudaMemcpyHostToDevice));
+                CUDA_OK(cudaMemcpy(d_roots, roots.data(), sizeof(int3) * roots.size(), cudaMemcpyHostToDevice));
+                CUDA_OK(cudaMemcpy(d_list, root_ids.data(), sizeof(int) * root_ids.size(), cudaMemcpyHostToDevice));
+                k_lbvh_permute<<<(unsigned)C, 128>>>(d_perm, d_idx2, d_idx);
+                std::swap(d_idx, d_idx2);                         // d_idx2 stays "the sorted order" for everything below
+                const int n_w = (int)std::max(rec.size() / 5, roots.size());
+                k_lbvh_write_top<<<(unsigned)((n_w + 255) / 256), 256>>>(d_rec, (int)(rec.size() / 5), d_roots, (int)roots.size(), N);
+                n_list = (int)root_ids.size();
+                top_done = true;
+            }
+        }
+        if (!top_done) {
+            k_lbvh_treelet_roots<<<gb, 256>>>(n, N, IRIS_SAH_TREELET, d_list, d_nlist);
+            CUDA_OK(cudaMemcpy(&n_list, d_nlist, sizeof(int), cudaMemcpyDeviceToHost));
+        }
         if (n_list > 0) {
             CUDA_OK(cudaFuncSetAttribute(k_lbvh_sah_treelets<IRIS_SAH_TREELET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SAH_SMEM_BYTES(IRIS_SAH_TREELET)));
             k_lbvh_sah_treelets<IRIS_SAH_TREELET><<<(unsigned)std::min(n_list, 148 * 16), SAH_THREADS, SAH_SMEM_BYTES(IRIS_SAH_TREELET)>>>(d_list, n_list, n, N, d_tbox, d_idx2);
@@ -236,7 +314,7 @@ done:
     cudaFree(d_verts); cudaFree(d_faces); cudaFree(d_recs); cudaFree(d_tris); cudaFree(d_tbox); cudaFree(d_bounds);
     cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_tmp);
     cudaFree(N.child); cudaFree(N.range); cudaFree(N.parent); cudaFree(N.box); cudaFree(N.flag);
-    cudaFree(d_wide); cudaFree(d_wide_bin); cudaFree(d_wide_depth); cudaFree(d_counters); cudaFree(d_list); cudaFree(d_nlist);
+    cudaFree(d_wide); cudaFree(d_wide_bin); cudaFree(d_wide_depth); cudaFree(d_counters); cudaFree(d_list); cudaFree(d_nlist); cudaFree(d_rec); cudaFree(d_cl); cudaFree(d_perm); cudaFree(d_roots); cudaFree(d_cbox);
     return e;
 }
 
@@ -275,6 +353,7 @@ int iris_set_option(const char *name, int value) {
     if (name && std::strcmp(name, "single_impl") == 0 && (value == 0 || value == 1)) { g_single_impl = value; return IRIS_OK; }
     if (name && std::strcmp(name, "single_chunk_log2") == 0 && value >= 10 && value <= 30) { g_single_chunk = (int64_t)1 << value; return IRIS_OK; }
     if (name && std::strcmp(name, "persist_ctas_per_sm") == 0 && value >= 1 && value <= 16) { g_persist_ctas = value; return IRIS_OK; }
+    if (name && std::strcmp(name, "lbvh_sah_top") == 0 && (value == 0 || value == 1)) { g_sah_top = value; return IRIS_OK; }
     if (name && std::strcmp(name, "lbvh_sah_treelets") == 0 && (value == 0 || value == 1)) { g_sah_treelets = value; return IRIS_OK; }
     if (name && std::strcmp(name, "tc5_bwd_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_tc5_bwd_ctas = value; return IRIS_OK; }
     if (name && std::strcmp(name, "scatter_ctas_per_sm") == 0 && value >= 0 && value <= 8) { g_scatter_ctas = value; return IRIS_OK; }

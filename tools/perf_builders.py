@@ -15,7 +15,10 @@ for irregular in (False, True):
     rays = torch.as_tensor(sc.camera_rays(1280, 960, view=1))[:262144 * 2].to(dev)
     n = rays.shape[0] * spp
     ws = torch.empty(lib.iris_single_workspace_bytes(rays.shape[0], spp), dtype=torch.uint8, device=dev)
-    for builder in (0, 1):
+    for builder, treelets, top, label in ((0, 1, 1, "host binned SAH"), (1, 0, 0, "device: Morton LBVH"), (1, 1, 0, "device: LBVH top, SAH treelets"),
+                                          (1, 1, 1, "device: SAH top + SAH treelets")):
+        core.C.check(lib.iris_set_option(b"lbvh_sah_treelets", treelets))
+        core.C.check(lib.iris_set_option(b"lbvh_sah_top", top))
         t0 = time.time()
         scene = core.Scene(sc.vertices, sc.faces, 0, builder=builder)
         tb = time.time() - t0
@@ -38,7 +41,7 @@ for irregular in (False, True):
             lib.iris_profile_read(k, ctypes.byref(c), ctypes.byref(t), 1)
             if c.value: out[nm.decode()] = t.value / 3
         lib.iris_profile_enable(0)
-        print("%-9s builder %d (%s)  build %.2f s  nodes %d depth %d | primary %.2f G rays/s  trace_queue %.2f G rays/s  forward %.1f M samples/s"
-              % ("irregular" if irregular else "regular", builder, "host SAH" if builder == 0 else "device LBVH", tb, st["n_nodes"], st["max_depth"],
+        print("%-9s %-32s build %.2f s (library %.0f ms)  nodes %d depth %d | primary %.2f G rays/s  trace_queue %.2f G rays/s  forward %.1f M samples/s"
+              % ("irregular" if irregular else "regular", label, tb, st["build_ms"], st["n_nodes"], st["max_depth"],
                  n / out["k_primary"] / 1e6, 2 * n / out["k_trace_queue"] / 1e6, n / sum(out.values()) / 1e3))
         del scene
