@@ -259,7 +259,7 @@ class Ctx:
         key = "c1" if w.get("cornell") else (w["tris"], bool(w.get("irregular")))
         if key not in self.scenes:
             sc = scenes.cornell() if w.get("cornell") else scenes.room(w["tris"], w["emitters"], seed=0, irregular=bool(w.get("irregular")))
-            scene = core.Scene(sc.vertices, sc.faces, self.local)
+            scene = core.Scene(sc.vertices, sc.faces, self.local, builder=os.environ.get("IRIS_BENCH_BUILDER", "auto"))   # A/B only: "sah" / "lbvh"
             tables = core.ShadingTables.from_dicts(self.dev, sc.emitter_dict(), sc.slf_dict(256), bench_params(), sc.voxel_bounds())
             self.scenes[key] = (sc, scene, scene.stats(), tables)
         return self.scenes[key]
@@ -589,6 +589,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     ctx = Ctx()
+    if os.environ.get("IRIS_BENCH_OPTIONS"):          # A/B runs only: "name=value,name=value" -> iris_set_option (the defaults are what is benchmarked)
+        from iris_b200 import core as _core
+        for kv in os.environ["IRIS_BENCH_OPTIONS"].split(","):
+            k, v = kv.split("=")
+            _core.C.check(_core.C.lib().iris_set_option(k.strip().encode(), int(v)))
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=ctx.dev)

@@ -101,4 +101,4 @@ struct HostBvh {
 int host_bvh_build(const float *verts, int64_t n_verts, const int32_t *faces, int64_t n_faces, HostBvh *out);
 void host_bvh_free(HostBvh *b);
 // SAH tree over C cluster boxes (6 floats each) for the top of the device builder's tree; see bvh_build.cpp.
-int host_sah_top(const float *boxes, int32_t C, int32_t *order, int32_t *first, int32_t *count, int32_t *nleft, int32_t *left, int32_t *right);
+int host_sah_top(const float *boxes, const int32_t *sizes, int32_t C, int32_t *order, int32_t *first, int32_t *count, int32_t *nleft, int32_t *left, int32_t *right);

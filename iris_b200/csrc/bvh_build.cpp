@@ -37,6 +37,7 @@ constexpr int kMaxLeaf = IRIS_MAX_LEAF;
 
 struct Builder {
     int32_t max_leaf = kMaxLeaf;   // 1: split down to single primitives (top tree over clusters, host_sah_top)
+    std::vector<int32_t> weight;   // optional: primitives behind each box (clusters); empty = 1 each.  Only the SAH cost uses it.
     std::vector<Box> tbox;
     std::vector<float> cent;   // 3 per tri
     std::vector<int32_t> order;
@@ -75,7 +76,7 @@ struct Builder {
                     int32_t t = order[i];
                     int k = std::min(kBins - 1, std::max(0, (int)((cent[3 * (size_t)t + ax] - c0) * scale)));
                     bb[k].grow(tbox[t]);
-                    bc[k]++;
+                    bc[k] += weight.empty() ? 1 : weight[(size_t)t];
                 }
                 float ra[kBins];
                 int32_t rc[kBins];
@@ -323,10 +324,11 @@ void host_bvh_free(HostBvh *b) {
 // most IRIS_SAH_TREELET primitives -- a few hundred to a few thousand boxes), split down to single clusters.  Returns the clusters in
 // tree order (`order`, C entries) and the internal nodes in pre-order: node k covers order[first[k] .. first[k] + count[k]) and splits
 // after its first nleft[k] clusters; left[k] / right[k] = index of the child node, or -1 - (position in order) when the child is one cluster.
-int host_sah_top(const float *boxes, int32_t C, int32_t *order, int32_t *first, int32_t *count, int32_t *nleft, int32_t *left, int32_t *right) {
+int host_sah_top(const float *boxes, const int32_t *sizes, int32_t C, int32_t *order, int32_t *first, int32_t *count, int32_t *nleft, int32_t *left, int32_t *right) {
     if (C < 2) return 0;
     Builder B;
     B.max_leaf = 1;
+    if (sizes) B.weight.assign(sizes, sizes + C);              // SAH cost = area x PRIMITIVES on each side, not clusters
     B.tbox.resize((size_t)C);
     B.cent.resize((size_t)C * 3);
     B.order.resize((size_t)C);

@@ -178,6 +178,7 @@ __global__ void k_lbvh_treelet_roots(int n, LbvhNodes N, int T, int *list, int *
     list[atomicAdd(count, 1)] = i;
 }
 
+// ---- optional (iris_set_option lbvh_sah_top 1; off by default: measured slower on whole interior views)
 // ---- top of the tree: the maximal subtrees of <= T primitives ("clusters", single leaves included) tile the sorted array; their boxes
 //      go to the host, which builds a SAH tree over the few hundred / thousand of them (host_sah_top) and sends back the new cluster
 //      order and the top nodes; the clusters are moved to their new places and the top nodes re-linked with the radix-tree numbering.

@@ -89,7 +89,8 @@ static int g_bake_impl = 2;        // 2: persistent warps with the generator / r
 static int g_wave_impl = 1;        // 1: wavefront bounces through the ray queue, 0: fused k_wave_bounce_a
 static int g_wave_compact = 1;     // 1: live-lane lists (dense queues, dead lanes cost nothing), 0: every kernel over all lanes (A/B)
 static int g_intersect_impl = 0;   // 1: persistent warps with dynamic ray fetch (k_intersect_persistent)
-static int g_sah_top = 1;          // device builder: SAH tree over the clusters for the levels above the treelets (host, tiny); 0 = Morton splits
+static int g_sah_top = 0;          // device builder: 1 = SAH tree over the clusters for the levels above the treelets (host, tiny); 0 = Morton splits
+                                   // (default: over whole interior views the Morton top traces 3-7 % faster than the SAH top, profiles/r2t_*)
 static int g_sah_treelets = 1;     // device builder: rebuild the lower levels with a binned SAH (bvh_device.cuh); 0 = plain LBVH
 static int g_tc5_bwd_ctas = 2;     // fused field adjoint: CTAs per SM (98 KB of shared memory each)
 static int g_scatter_ctas = 0;     // > 0: cap the grid of the grid-gradient scatter at this many CTAs per SM (it strides over the samples)
@@ -213,7 +214,7 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
             k_lbvh_cluster_boxes<<<(unsigned)(((size_t)C * 32 + 255) / 256), 256>>>(d_cl, C, d_tbox, d_idx2, d_cbox);
             CUDA_OK(cudaMemcpy(cl.data(), d_cl, sizeof(int2) * (size_t)C, cudaMemcpyDeviceToHost));
             CUDA_OK(cudaMemcpy(cbox.data(), d_cbox, sizeof(float) * 6 * (size_t)C, cudaMemcpyDeviceToHost));
-            std::vector<int32_t> by_start((size_t)C);
+            std::vector<int32_t> by_start((size_t)C), ssize((size_t)C);
             for (int c = 0; c < C; ++c) by_start[(size_t)c] = c;
             std::sort(by_start.begin(), by_start.end(), [&](int32_t x, int32_t y) { return cl[(size_t)x].x < cl[(size_t)y].x; });
             bool tiles = true;                                   // the clusters must tile [0, n) exactly
@@ -223,11 +224,12 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
                 tiles = q.x == pos && q.y >= 1;
                 pos += q.y;
                 for (int k = 0; k < 6; ++k) sbox[6 * (size_t)c + k] = cbox[6 * (size_t)by_start[(size_t)c] + k];
+                ssize[(size_t)c] = q.y;
             }
             tiles = tiles && pos == n;
             if (tiles) {
                 std::vector<int32_t> order((size_t)C), tf((size_t)C), tc((size_t)C), tl((size_t)C), tL((size_t)C), tR((size_t)C);
-                const int n_top = host_sah_top(sbox.data(), C, order.data(), tf.data(), tc.data(), tl.data(), tL.data(), tR.data());
+                const int n_top = host_sah_top(sbox.data(), ssize.data(), C, order.data(), tf.data(), tc.data(), tl.data(), tL.data(), tR.data());
                 std::vector<int64_t> P((size_t)C + 1, 0);        // first sorted position of the cluster at tree-order position k
                 std::vector<int3> perm((size_t)C), roots;
                 for (int k = 0; k < C; ++k) {

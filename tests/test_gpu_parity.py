@@ -755,13 +755,22 @@ def test_device_lbvh_builder_gives_identical_hits():
     dev = _gpu()
     from iris_b200 import core, scenes
     from oracle.intersect import OracleScene
-    for sc in (scenes.cornell(), scenes.room(200_000, 16, seed=3)):
+    lib = core.C.lib()
+    for sc in (scenes.cornell(), scenes.room(200_000, 16, seed=3), scenes.room(120_000, 16, seed=4, irregular=True)):
         osc = OracleScene(sc.vertices, sc.faces)
-        scene = core.Scene(sc.vertices, sc.faces, 0, builder=1)
-        st = scene.stats()
-        assert st["n_tris"] == sc.n_tris and 0 < st["max_depth"] <= 24 and st["n_nodes"] < sc.n_tris
         o, d = _rays_for_parity(sc, osc, 60_000, 7)
-        _check_intersect(scene, osc, o, d, dev)
+        try:
+            # every form of the device builder: plain Morton LBVH, SAH treelets below a Morton top (default), SAH top + SAH treelets
+            for treelets, top in ((0, 0), (1, 0), (1, 1)):
+                core.C.check(lib.iris_set_option(b"lbvh_sah_treelets", treelets))
+                core.C.check(lib.iris_set_option(b"lbvh_sah_top", top))
+                scene = core.Scene(sc.vertices, sc.faces, 0, builder=1)
+                st = scene.stats()
+                assert st["n_tris"] == sc.n_tris and 0 < st["max_depth"] <= 24 and st["n_nodes"] < sc.n_tris, (treelets, top, st)
+                _check_intersect(scene, osc, o, d, dev)
+        finally:
+            core.C.check(lib.iris_set_option(b"lbvh_sah_treelets", 1))
+            core.C.check(lib.iris_set_option(b"lbvh_sah_top", 0))
     v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
     for faces in (np.array([[0, 1, 2]], np.int32), np.array([[0, 1, 2], [0, 1, 3]], np.int32), np.array([[0, 1, 2]] * 5, np.int32)):
         scene = core.Scene(v, faces, 0, builder=1)                      # 1, 2 and 5 (coincident) triangles

@@ -12,7 +12,11 @@ spp = 32
 for irregular in (False, True):
     sc = scenes.room(1_000_000, 16, seed=0, irregular=irregular)
     tables = core.ShadingTables.from_dicts(dev, sc.emitter_dict(), sc.slf_dict(256), params, sc.voxel_bounds())
-    rays = torch.as_tensor(sc.camera_rays(1280, 960, view=1))[:262144 * 2].to(dev)
+    views = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1]
+    rays = torch.cat([torch.as_tensor(sc.camera_rays(1280, 960, view=v)) for v in views])
+    if len(views) == 1:
+        rays = rays[:262144 * 2]
+    rays = rays.to(dev)
     n = rays.shape[0] * spp
     ws = torch.empty(lib.iris_single_workspace_bytes(rays.shape[0], spp), dtype=torch.uint8, device=dev)
     for builder, treelets, top, label in ((0, 1, 1, "host binned SAH"), (1, 0, 0, "device: Morton LBVH"), (1, 1, 0, "device: LBVH top, SAH treelets"),
