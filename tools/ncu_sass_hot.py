@@ -15,9 +15,11 @@ col = {n: i for i, n in enumerate(hdr)}
 S, I, T, W = col["Source"], col["Instructions Executed"], col["Thread Instructions Executed"], col["Warp Stall Sampling (All Samples)"]
 ops = collections.defaultdict(lambda: [0, 0, 0])
 lines = []
+seen = set()
 for r in rows[h + 1:]:
-    if len(r) <= max(S, I, T, W):
+    if len(r) <= max(S, I, T, W) or r[0] in seen:       # (the export lists every address once per view: keep the first)
         continue
+    seen.add(r[0])
     src = r[S].strip()
     tok = src.split()
     op = tok[1] if tok and tok[0].startswith("@") and len(tok) > 1 else (tok[0] if tok else "?")
