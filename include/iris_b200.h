@@ -48,8 +48,10 @@ int64_t iris_abi_info(int what);
  * Scene: one triangle mesh + 8-wide compressed BVH resident in HBM.
  * Replaces mitsuba.load_dict({'type':'scene','shape_id':{'type':'obj'|'ply',...}})
  * (train_emitter.py:57-63, bake_shading.py:55-61); prim index = face order of `faces`.
- * verts/faces are HOST pointers.  builder: 1 = on-device Morton LBVH -> 8-wide collapse (15 ms per 1M triangles; what the Python layer
- * uses), 0 = host binned-SAH (0.7 s per 1M triangles).
+ * verts/faces are HOST pointers.  builder: 1 = on the device (what the Python layer uses): Morton hierarchy, every subtree of <= 4096
+ * primitives rebuilt with a binned SAH in shared memory, collapse to 8-wide -- 25-100 ms for 1M-5M triangles, ray rates of a host SAH tree
+ * also on irregular scan-like meshes (iris_set_option "lbvh_sah_treelets" 0 = plain LBVH, "lbvh_sah_top" 1 = SAH over the clusters for
+ * the top levels as well); 0 = host binned SAH (0.7-1 s per 1M triangles).  Hits do not depend on the builder.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct IrisScene IrisScene;
 
@@ -292,7 +294,10 @@ int64_t iris_launch_count(void);
  *   "bake_impl"               2 persistent kernel, generator and radiance lookup inside | 0 fused kernel with block-level direction sort | 1 ray queue
  *   "intersect_impl"          0 one ray per lane (best on camera rays) | 1 persistent warps with dynamic ray fetch (best on incoherent rays)
  *   "persist_ctas_per_sm"     8: resident CTAs per SM of the persistent kernels (1..16)
- *   "tc5_ctas_per_sm" 4, "field_smem_carveout_pct" 70, "trace_smem_carveout_pct" -1: occupancy / L1 tuning of the field and tracing kernels
+ *   "lbvh_sah_treelets"       1 device builder rebuilds subtrees of <= 4096 primitives with a binned SAH | 0 plain Morton LBVH
+ *   "lbvh_sah_top"            0 Morton splits above the treelets | 1 SAH tree over the clusters (slower over whole interior views)
+ *   "tc5_ctas_per_sm" 4, "tc5_bwd_ctas_per_sm" 2, "scatter_ctas_per_sm" 0 (uncapped), "field_smem_carveout_pct" 70, "trace_smem_carveout_pct" -1:
+ *                             occupancy / L1 tuning of the field and tracing kernels (measurement knobs)
  * Unknown names or out-of-range values return IRIS_ERR_INVALID. */
 int iris_set_option(const char *name, int value);
 
