@@ -107,6 +107,8 @@ struct LbvhNodes {
     int2 *range;      // internal: [first,last] sorted leaf range
     DBox *box;        // all 2n-1 nodes (padded)
     int *flag;        // internal: arrival counter
+    float *cost;      // internal: 8 per node, cost[i] = C(node, i) for i = 1..7 (see k_lbvh_fit)
+    uint32_t *dec;    // internal: the decisions behind cost[]
 };
 
 __device__ __forceinline__ int lbvh_delta(const unsigned long long *__restrict__ keys, int n, int i, int j) {
@@ -404,6 +406,68 @@ __global__ void __launch_bounds__(SAH_THREADS) k_lbvh_sah_treelets(const int *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// SAH-optimal collapse to 8-wide (Ylitie, Karras, Laine 2017, section 3.1), computed bottom-up next to the boxes:
+//   C(n, i) = least cost of turning the subtree of binary node n into AT MOST i children of a wide node, i = 1..7
+//   C(n, 1) = min( leaf: A_n P_n c_prim  (P_n <= 3 triangles),  inner wide node: A_n c_node + D(n, 8) )
+//   C(n, i) = min( D(n, i), C(n, i - 1) ),   D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// dec packs the argmins: bits [3(j-2), 3(j-2)+3) = k for D(n, j), j = 2..8; bit 21 + (i-2) = "C(n,i) is C(n,i-1)", i = 2..7; bit 27 = leaf.
+// k_lbvh_collapse then expands every wide node along these decisions instead of greedily opening the child of largest area.
+// ------------------------------------------------------------------------------------------------------------------------
+#ifndef IRIS_COLLAPSE_DP
+#define IRIS_COLLAPSE_DP 1
+#endif
+#ifndef IRIS_SAH_CPRIM
+#define IRIS_SAH_CPRIM 0.6f       // cost of one triangle test relative to one 8-wide node visit
+#endif
+__device__ __forceinline__ float dbox_area(const DBox &b);
+__device__ __forceinline__ void lbvh_child_costs(const LbvhNodes &N, int n, int node, float area, float c[8]) {
+    if (node >= n - 1) {                                        // a single triangle: one leaf slot whatever i is
+#pragma unroll
+        for (int i = 1; i < 8; ++i) c[i] = area * IRIS_SAH_CPRIM;
+    } else {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) c[i] = __ldcg(N.cost + 8 * (size_t)node + i);      // (written by another thread of this launch: read at L2)
+    }
+}
+__device__ __forceinline__ void lbvh_collapse_cost(const LbvhNodes &N, int n, int p, int2 ch, float area_l, float area_r, float area_p) {
+    float cl[8], cr[8], D[9];
+    lbvh_child_costs(N, n, ch.x, area_l, cl);
+    lbvh_child_costs(N, n, ch.y, area_r, cr);
+    uint32_t dec = 0;
+#pragma unroll
+    for (int j = 2; j <= 8; ++j) {
+        float best = INFINITY;
+        int bk = 1;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            if (k >= j || j - k > 7) continue;
+            const float v = cl[k] + cr[j - k];
+            if (v < best) { best = v; bk = k; }
+        }
+        D[j] = best;
+        dec |= (uint32_t)bk << (3 * (j - 2));
+    }
+    const int2 r = N.range[p];
+    const int cnt = r.y - r.x + 1;
+    float c1 = area_p + D[8];
+    if (cnt <= IRIS_MAX_LEAF) {
+        const float leaf = area_p * (float)cnt * IRIS_SAH_CPRIM;
+        if (leaf <= c1) { c1 = leaf; dec |= 1u << 27; }
+    }
+    float *C = N.cost + 8 * (size_t)p;
+    C[1] = c1;
+    float prev = c1;
+#pragma unroll
+    for (int i = 2; i < 8; ++i) {
+        float v = D[i];
+        if (prev <= v) { v = prev; dec |= 1u << (21 + (i - 2)); }
+        C[i] = v;
+        prev = v;
+    }
+    N.dec[p] = dec;
+}
+
 __global__ void k_lbvh_fit(const DBox *__restrict__ tbox, const uint32_t *__restrict__ sorted, int n, const float *__restrict__ bounds, LbvhNodes N) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -426,6 +490,9 @@ __global__ void k_lbvh_fit(const DBox *__restrict__ tbox, const uint32_t *__rest
         const DBox x = N.box[c.x], y = N.box[c.y];
         for (int a = 0; a < 3; ++a) { b.lo[a] = fminf(x.lo[a], y.lo[a]); b.hi[a] = fmaxf(x.hi[a], y.hi[a]); }
         N.box[p] = b;
+#if IRIS_COLLAPSE_DP
+        lbvh_collapse_cost(N, n, p, c, dbox_area(x), dbox_area(y), dbox_area(b));
+#endif
         p = N.parent[p];
     }
 }
@@ -457,6 +524,34 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
     const int bnode = wide_bin[w];
     int ch[8];
     int nch = 0;
+#if IRIS_COLLAPSE_DP
+    bool leaf_ch[8];                                         // child i is a leaf slot (<= 3 triangles) rather than a wide node of its own
+    if (bnode >= n - 1 || ((N.dec[bnode] >> 27) & 1u)) {
+        leaf_ch[nch] = true;
+        ch[nch++] = bnode;                                   // tiny scene: the root itself is a leaf child
+    } else {
+        int st_node[8], st_i[8], sp = 0;
+        st_node[sp] = bnode; st_i[sp] = 8; ++sp;             // distribute the root over 8 slots
+        bool root = true;
+        while (sp > 0) {
+            --sp;
+            const int nd = st_node[sp];
+            int i = st_i[sp];
+            if (nd >= n - 1) { leaf_ch[nch] = true; ch[nch++] = nd; continue; }       // a single triangle
+            const uint32_t dec = N.dec[nd];
+            if (!root) {
+                while (i > 1 && ((dec >> (21 + (i - 2))) & 1u)) --i;                    // C(nd, i) = C(nd, i - 1)
+                if (i == 1) { leaf_ch[nch] = (dec >> 27) & 1u; ch[nch++] = nd; continue; }
+            }
+            root = false;
+            const int k = (int)((dec >> (3 * (i - 2))) & 7u);
+            const int2 c = N.child[nd];
+            st_node[sp] = c.y; st_i[sp] = i - k; ++sp;       // (right pushed first: the left subtree comes out first)
+            st_node[sp] = c.x; st_i[sp] = k; ++sp;
+        }
+    }
+#define LBVH_IS_INNER(i) (!leaf_ch[i])
+#else
     if (lbvh_count(N, n, bnode) <= IRIS_MAX_LEAF) {
         ch[nch++] = bnode;                                   // tiny scene: the root itself is a leaf child
     } else {
@@ -477,6 +572,8 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
             ch[nch++] = c2.y;
         }
     }
+#define LBVH_IS_INNER(i) (lbvh_count(N, n, ch[i]) > IRIS_MAX_LEAF)
+#endif
     DBox nb;
     for (int a = 0; a < 3; ++a) { nb.lo[a] = INFINITY; nb.hi[a] = -INFINITY; }
     for (int i = 0; i < nch; ++i) {
@@ -507,7 +604,7 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
     int n_inner = 0, n_tris = 0;
     for (int i = 0; i < nch; ++i) {
         const int c = lbvh_count(N, n, ch[i]);
-        if (c > IRIS_MAX_LEAF) ++n_inner; else n_tris += c;
+        if (LBVH_IS_INNER(i)) ++n_inner; else n_tris += c;
     }
     const int child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0;
     const int tri_base = n_tris ? atomicAdd(&counters[1], n_tris) : 0;
@@ -533,7 +630,7 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
             qhi[a][s] = bvh8_encode_q((int)fmax(0.0, fmin((double)BVH8_QMAX, ceil(((double)b.hi[a] - (double)O.p[a]) / sc))));
         }
         const int c = lbvh_count(N, n, ch[i]);
-        if (c > IRIS_MAX_LEAF) {
+        if (LBVH_IS_INNER(i)) {
             O.imask |= (uint8_t)(1u << s);
             O.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             wide_bin[child_base + inner_i] = ch[i];

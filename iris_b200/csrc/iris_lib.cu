@@ -190,6 +190,8 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
     CUDA_OK(cudaMalloc(&N.parent, sizeof(int) * 2 * (size_t)n));
     CUDA_OK(cudaMalloc(&N.box, sizeof(DBox) * 2 * (size_t)n));
     CUDA_OK(cudaMalloc(&N.flag, sizeof(int) * (size_t)n));
+    CUDA_OK(cudaMalloc(&N.cost, sizeof(float) * 8 * (size_t)n));
+    CUDA_OK(cudaMalloc(&N.dec, sizeof(uint32_t) * (size_t)n));
     CUDA_OK(cudaMemset(N.flag, 0, sizeof(int) * (size_t)n));
     CUDA_OK(cudaMemset(N.parent, 0xFF, sizeof(int) * 2 * (size_t)n));
     if (n > 1) k_lbvh_hierarchy<<<gb, 256>>>(d_keys2, n, N);
@@ -315,7 +317,7 @@ static cudaError_t device_bvh_build(const float *verts, int64_t n_verts, const i
 done:
     cudaFree(d_verts); cudaFree(d_faces); cudaFree(d_recs); cudaFree(d_tris); cudaFree(d_tbox); cudaFree(d_bounds);
     cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_tmp);
-    cudaFree(N.child); cudaFree(N.range); cudaFree(N.parent); cudaFree(N.box); cudaFree(N.flag);
+    cudaFree(N.child); cudaFree(N.range); cudaFree(N.parent); cudaFree(N.box); cudaFree(N.flag); cudaFree(N.cost); cudaFree(N.dec);
     cudaFree(d_wide); cudaFree(d_wide_bin); cudaFree(d_wide_depth); cudaFree(d_counters); cudaFree(d_list); cudaFree(d_nlist); cudaFree(d_rec); cudaFree(d_cl); cudaFree(d_perm); cudaFree(d_roots); cudaFree(d_cbox);
     return e;
 }
