@@ -49,7 +49,7 @@ int64_t iris_abi_info(int what);
  * Replaces mitsuba.load_dict({'type':'scene','shape_id':{'type':'obj'|'ply',...}})
  * (train_emitter.py:57-63, bake_shading.py:55-61); prim index = face order of `faces`.
  * verts/faces are HOST pointers.  builder: 1 = on the device (what the Python layer uses): Morton hierarchy, every subtree of <= 4096
- * primitives rebuilt with a binned SAH in shared memory, collapse to 8-wide -- 25-100 ms for 1M-5M triangles, ray rates of a host SAH tree
+ * primitives rebuilt with a binned SAH in shared memory, SAH-optimal collapse to 8-wide -- 25-100 ms for 1M-5M triangles, ray rates of a host SAH tree
  * also on irregular scan-like meshes (iris_set_option "lbvh_sah_treelets" 0 = plain LBVH, "lbvh_sah_top" 1 = SAH over the clusters for
  * the top levels as well); 0 = host binned SAH (0.7-1 s per 1M triangles).  Hits do not depend on the builder.
  * ---------------------------------------------------------------------------------------------- */
