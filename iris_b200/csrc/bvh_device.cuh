@@ -414,6 +414,9 @@ __global__ void __launch_bounds__(SAH_THREADS) k_lbvh_sah_treelets(const int *__
 // dec packs the argmins: bits [3(j-2), 3(j-2)+3) = k for D(n, j), j = 2..8; bit 21 + (i-2) = "C(n,i) is C(n,i-1)", i = 2..7; bit 27 = leaf.
 // k_lbvh_collapse then expands every wide node along these decisions instead of greedily opening the child of largest area.
 // ------------------------------------------------------------------------------------------------------------------------
+#ifndef IRIS_SLOT_2OPT
+#define IRIS_SLOT_2OPT 1
+#endif
 #ifndef IRIS_COLLAPSE_DP
 #define IRIS_COLLAPSE_DP 1
 #endif
@@ -601,6 +604,26 @@ __global__ void k_lbvh_collapse(int begin, int end, int n, LbvhNodes N, const Tr
         slot_of[bi] = bs;
         child_in_slot[bs] = bi;
     }
+#if IRIS_SLOT_2OPT
+    // pairwise improvement of the greedy assignment: exchange the contents of two slots (children or holes) while the total cost drops
+    for (int pass = 0; pass < 4; ++pass) {
+        bool any = false;
+        for (int s0 = 0; s0 < 8; ++s0)
+            for (int s1 = s0 + 1; s1 < 8; ++s1) {
+                const int i0 = child_in_slot[s0], i1 = child_in_slot[s1];
+                if (i0 < 0 && i1 < 0) continue;
+                const float cur = (i0 >= 0 ? cost[i0][s0] : 0.f) + (i1 >= 0 ? cost[i1][s1] : 0.f);
+                const float alt = (i0 >= 0 ? cost[i0][s1] : 0.f) + (i1 >= 0 ? cost[i1][s0] : 0.f);
+                if (alt < cur) {
+                    child_in_slot[s0] = i1; child_in_slot[s1] = i0;
+                    if (i0 >= 0) slot_of[i0] = s1;
+                    if (i1 >= 0) slot_of[i1] = s0;
+                    any = true;
+                }
+            }
+        if (!any) break;
+    }
+#endif
     int n_inner = 0, n_tris = 0;
     for (int i = 0; i < nch; ++i) {
         const int c = lbvh_count(N, n, ch[i]);
