@@ -1,4 +1,4 @@
-// bvh_device.cuh -- on-device builder (builder = 1): Morton-ordered LBVH (Karras 2012) -> greedy collapse to 8-wide ->
+// bvh_device.cuh -- on-device builder (builder = 1): Morton-ordered LBVH (Karras 2012) -> SAH treelets -> SAH-optimal collapse to 8-wide ->
 // octant slot assignment -> conservative 8-bit quantisation, producing exactly the node / triangle layout of bvh8.h.
 // Milliseconds instead of the host builder's ~0.7 s per million triangles.  The lower levels (subtrees of <= IRIS_SAH_TREELET
 // primitives) are rebuilt with a binned SAH in shared memory (k_lbvh_sah_treelets); the levels above them are the Morton splits.

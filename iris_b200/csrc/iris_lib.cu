@@ -415,7 +415,7 @@ int iris_scene_create(const float *verts, int64_t n_verts, const int32_t *faces,
     *out = nullptr;
     if (n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!verts || !faces))) return fail(IRIS_ERR_INVALID, "bad mesh arguments");
     if (n_faces > 0x7FFFFFF0ll / 3) return fail(IRIS_ERR_INVALID, "too many faces");
-    if (builder != 0 && builder != 1) return fail(IRIS_ERR_INVALID, "builder must be 0 (host binned SAH) or 1 (on-device LBVH)");
+    if (builder != 0 && builder != 1) return fail(IRIS_ERR_INVALID, "builder must be 0 (host binned SAH) or 1 (on-device builder)");
     for (int64_t i = 0; i < 3 * n_faces; ++i)
         if (faces[i] < 0 || faces[i] >= n_verts) return fail(IRIS_ERR_INVALID, "face index out of range");
     CUDA_TRY(cudaSetDevice(device));
