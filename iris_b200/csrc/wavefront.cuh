@@ -296,11 +296,19 @@ __global__ void __launch_bounds__(IRIS_BLOCK) k_wave_gen(IrisShadeParams P, Iris
         W.S7[i] = make_float4(w0, w0, w0, 0.f);
         W.S8[i] = make_float4(w1, w1, w1, 0.f);
     }
+    float4 ro_b = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
+#ifndef IRIS_NO_RAY_SKIP
+    // rays that cannot change the result are not cast (as in k_single_gen): a shadow ray whose pending contribution is exactly zero
+    // (emitter below the horizon), and -- with NEE, where everything the path gathers from here on is multiplied by it -- a BSDF ray
+    // whose weight is exactly zero: the resolve step sees a miss, which ends the path with nothing added
+    if (KIND <= 1 && is_zero3(pend)) { ro_s = empty; rd_s = empty; }
+    if (KIND <= 1 && is_zero3(bw)) ro_b = empty;
+#endif
     if (KIND <= 1) {
         W.RO[j] = ro_s;
         W.RD[j] = rd_s;
     }
-    W.RO[off + j] = ray4(ray_origin(x0, wi), __int_as_float(0x7f800000));
+    W.RO[off + j] = ro_b;
     W.RD[off + j] = make_float4(wi.x, wi.y, wi.z, __int_as_float(-1));
     W.PN[j] = make_float4(pend.x, pend.y, pend.z, bpdf);
 }
