@@ -219,6 +219,10 @@ __global__ void __launch_bounds__(IRIS_BLOCK, 8) k_bake_persistent(SceneView S, 
                     }
                     trav_init(T, ray_origin(x, wi), wi,
                               __int_as_float(0x7f800000), -1, 0);
+#ifndef IRIS_NO_RAY_SKIP
+                    // a specular sample below the horizon has both weights exactly zero: whatever it hits adds nothing -> not traced
+                    if (MODE == 1 && w0 == 0.f && w1 == 0.f) { T.done = true; ray = -1; }
+#endif
                 }
             }
             if ((int64_t)base + cnt >= n) exhausted = true;
