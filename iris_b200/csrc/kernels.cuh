@@ -319,12 +319,14 @@ __global__ void __launch_bounds__(IRIS_BLOCK, IRIS_QUEUE_MINBLOCKS) k_trace_queu
             if (T.done) {
                 const int64_t r = (int64_t)base + __popc(need & ((1u << lane) - 1u));
                 if (r < n_rays) {
-                    const float4 a = ro[r];
-                    if (a.w >= 0.f) {
-                        const float4 b = rd[r];
-                        ray = r;
-                        trav_init(T, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, __float_as_int(b.w), r < n_anyhit ? 1 : 0);
-                    } else {
+                    // (no branch around trav_init: an empty slot is initialised like a ray and retired at once -- branching around the
+                    // inlined initialisation costs the compiler's code generation dearly, see k_bake_persistent)
+                    const float4 a = ro[r], b = rd[r];
+                    ray = r;
+                    trav_init(T, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, __float_as_int(b.w), r < n_anyhit ? 1 : 0);
+                    if (!(a.w >= 0.f)) {
+                        T.done = true;
+                        ray = -1;
                         hit[r] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
                     }
                 }
