@@ -363,13 +363,13 @@ __device__ __forceinline__ void trav_step(const SceneView &S, TravState &T, uint
         if (tri_test(T.o, T.d, T.rdd, v0, e1, e2, t, u, v)) {
             if (t < T.best.t || (t == T.best.t && prim < T.best.prim)) {
                 T.best.t = t; T.best.u = u; T.best.v = v; T.best.prim = prim; T.best.slot = slot;
-                if (T.anyhit) { T.done = true; return; }
+                if (T.anyhit) { T.done = true; break; }          // (no early return: one exit from the step)
             }
         }
     }
-    if (T.ngroup.y <= 0x00FFFFFFu) {
-        if (T.sp == 0) { T.done = true; return; }
-        T.ngroup = stack[--T.sp];
+    if (!T.done && T.ngroup.y <= 0x00FFFFFFu) {
+        if (T.sp == 0) T.done = true;
+        else T.ngroup = stack[--T.sp];
     }
 }
 
